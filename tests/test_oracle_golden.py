@@ -1,0 +1,71 @@
+"""Pins oracle/cloze_oracle.py to outputs of the reference's own module
+(tests/golden/cloze_tiny.npz, written by tests/golden/make_golden.py)."""
+import numpy as np
+import torch
+
+from oracle import cloze_oracle as oc
+
+
+def _tensors(d):
+    return {k: torch.as_tensor(np.ascontiguousarray(v)) for k, v in d.items()}
+
+
+def test_mask_matches_reference(golden):
+    cfg = golden["config"]
+    S = cfg["max_sequence_length"]
+    d = {k: v.reshape(-1, S) for k, v in _tensors(golden["batch"]).items()}
+    dm = oc.mask_batch(d, torch.as_tensor(golden["randval"]), cfg)
+    for k, ref in golden["masked"].items():
+        got = dm[k].reshape(-1).numpy()
+        assert got.dtype == ref.dtype, k
+        assert np.array_equal(got, ref), k
+
+
+def test_losses_and_grads_fp32(golden):
+    cfg = golden["config"]
+    p = _tensors(golden["param"])
+    losses, grads, _ = oc.step_with_grads(_tensors(golden["batch"]), p, cfg, torch.as_tensor(golden["randval"]),
+                                          golden["task_weights"])
+    np.testing.assert_allclose([float(x) for x in losses], golden["losses"], rtol=2e-5)
+    assert set(grads) == set(golden["grad"])
+    for k, ref in golden["grad"].items():
+        got = grads[k].numpy()
+        den = max(np.abs(ref).max(), 1e-12)
+        assert np.abs(got - ref).max() / den < 1e-4, (k, np.abs(got - ref).max() / den)
+
+
+def test_losses_bf16_autocast(golden):
+    cfg = golden["config"]
+    p = _tensors(golden["param"])
+    losses, grads, _ = oc.step_with_grads(_tensors(golden["batch"]), p, cfg, torch.as_tensor(golden["randval"]),
+                                          golden["task_weights"], autocast=True)
+    np.testing.assert_allclose([float(x) for x in losses], golden["losses_bf16"], rtol=2e-3)
+    for k, ref in golden["grad_bf16"].items():
+        got = grads[k].float().numpy()
+        rel = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-12)
+        assert rel < 2e-2, (k, rel)
+
+
+def test_eval_moments(golden):
+    cfg = golden["config"]
+    p = _tensors(golden["param"])
+    with torch.no_grad():
+        out, _ = oc.step(_tensors(golden["batch"]), p, cfg, torch.as_tensor(golden["randval"]), evaluate=True)
+    flat = []
+    for e in out:
+        flat += [float(x) for x in e] if isinstance(e, list) else [float(e)]
+    np.testing.assert_allclose(flat, golden["eval_flat"], rtol=2e-5)
+
+
+def test_jagged_offsets_and_block_permutation():
+    u = np.array([3, 3, 3, 1, 1, 7, 0, 0, 0, 0], dtype=np.int32)
+    off = oc.jagged_offsets(u)
+    assert off.tolist() == [0, 3, 5, 6, 10]
+    assert oc.jagged_offsets(np.zeros(0, np.int32)).tolist() == [0]
+    assert oc.jagged_offsets(np.array([5], np.int32)).tolist() == [0, 1]
+    perm = oc.block_permutation(off, [2, 0, 3, 1])
+    assert perm.tolist() == [5, 0, 1, 2, 6, 7, 8, 9, 3, 4]
+    # restates transformer.py:53-68 literally for a cross-check
+    change = np.where(u[:-1] != u[1:])[0] + 1
+    blocks = np.split(np.arange(len(u)), change)
+    assert np.concatenate([blocks[b] for b in [2, 0, 3, 1]]).tolist() == perm.tolist()
