@@ -1,0 +1,349 @@
+"""ctypes binding of libgraft.so (the C ABI in include/graft.h).
+
+Thin by design: tensors are unwrapped to raw device pointers and the current
+CUDA stream; nothing here computes.  There is no fallback: if the shared
+library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgraft.so")
+
+vp, i32, i64, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
+
+
+class GraftError(RuntimeError):
+    pass
+
+
+class ActionArgs(C.Structure):
+    _fields_ = [
+        ("time", vp), ("gender", vp), ("source", vp), ("status", vp), ("rating", vp), ("progress", vp),
+        ("periodic_cos", vp), ("periodic_sin", vp),
+        ("gender_table", vp), ("source_table", vp), ("status_table", vp),
+        ("gender_rows", C.c_int), ("source_rows", C.c_int), ("status_rows", C.c_int),
+        ("weight", vp), ("bias", vp),
+        ("min_ts", f64), ("max_ts", f64), ("rating_mean", f32), ("rating_std", f32),
+        ("n", i64), ("d", C.c_int), ("round_bf16", C.c_int),
+    ]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", vp), ("lda", i64), ("a_kmajor", C.c_int),
+        ("B", vp), ("ldb", i64), ("b_kmajor", C.c_int),
+        ("C", vp), ("ldc", i64),
+        ("M", i64), ("N", i64), ("K", i64),
+        ("epilogue", C.c_int),
+        ("resid", vp), ("ldr", i64),
+        ("bias", vp),
+        ("aux", vp), ("ldaux", i64),
+        ("ce_pmax", vp), ("ce_psum", vp), ("ce_tgt", vp), ("ce_target", vp), ("ce_lse", vp), ("ce_coef", vp),
+        ("n_offset", i32), ("split_k", C.c_int),
+    ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("qkv", vp), ("ld", i64), ("k_col", C.c_int), ("v_col", C.c_int),
+        ("H", C.c_int), ("G", C.c_int), ("rows", C.c_int), ("row_len", C.c_int),
+        ("userid_tok", vp), ("tm_tok", vp), ("seg_start", vp), ("seg_end", vp),
+    ]
+
+
+EPI_BF16, EPI_F32, EPI_F32_ACCUM, EPI_RESID, EPI_BIAS_BF16, EPI_BIAS_GELU, EPI_CE_PARTIAL, EPI_CE_GRAD, EPI_TABLE = range(9)
+
+_lib = None
+
+
+def load():
+    """Loads libgraft.so; raises GraftError when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GraftError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(there is no CPU or PyTorch fallback for the cloze step)")
+    lib = C.CDLL(LIB_PATH)
+    lib.graft_last_error.restype = C.c_char_p
+    lib.graft_scatter_add_scratch_bytes.restype = i64
+    lib.graft_gemm_scratch_bytes.restype = i64
+    _lib = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise GraftError(f"{what} failed ({rc}): {load().graft_last_error().decode()}")
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_contiguous() or t.numel() == 0, "graft: tensor must be contiguous"
+    return vp(t.data_ptr())
+
+
+def stream():
+    return vp(torch.cuda.current_stream().cuda_stream)
+
+
+def device_sms():
+    return load().graft_device_sms()
+
+
+_scratch = {}
+
+
+def scratch(nbytes, device, slot=0):
+    """Reused byte workspace (grows, never shrinks); one per (device, slot)."""
+    key = (str(device), slot)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------ packing --
+def jagged_offsets_host(userid_np):
+    import numpy as np
+    u = np.ascontiguousarray(userid_np, dtype=np.int32)
+    out = np.empty(u.size + 1, dtype=np.int64)
+    n = i64(0)
+    _check(load().graft_jagged_offsets_host(u.ctypes.data_as(vp), i64(u.size), out.ctypes.data_as(vp), C.byref(n)),
+           "graft_jagged_offsets_host")
+    return out[: n.value + 1].copy()
+
+
+def block_permutation_host(offsets_np, order_np):
+    import numpy as np
+    off = np.ascontiguousarray(offsets_np, dtype=np.int64)
+    order = np.ascontiguousarray(order_np, dtype=np.int64)
+    out = np.empty(int(off[-1]) if off.size else 0, dtype=np.int64)
+    _check(load().graft_block_permutation_host(off.ctypes.data_as(vp), i64(order.size), order.ctypes.data_as(vp),
+                                               out.ctypes.data_as(vp)), "graft_block_permutation_host")
+    return out
+
+
+def concat_pad_host(pieces, total):
+    import numpy as np
+    dt = pieces[0].dtype
+    pieces = [np.ascontiguousarray(p, dtype=dt) for p in pieces]
+    ptrs = (vp * len(pieces))(*[p.ctypes.data for p in pieces])
+    lens = (i64 * len(pieces))(*[p.size for p in pieces])
+    out = np.empty(total, dtype=dt)
+    _check(load().graft_concat_pad_host(ptrs, lens, i64(len(pieces)), i64(dt.itemsize), out.ctypes.data_as(vp), i64(total)),
+           "graft_concat_pad_host")
+    return out
+
+
+def jagged_offsets(userid):
+    n = userid.numel()
+    out = torch.empty(n + 1, dtype=torch.int64, device=userid.device)
+    cnt = torch.zeros(1, dtype=torch.int64, device=userid.device)
+    ws = scratch(4 * n + 16, userid.device)
+    _check(load().graft_jagged_offsets(ptr(userid), i64(n), ptr(out), ptr(cnt), ptr(ws), i64(ws.numel()), stream()),
+           "graft_jagged_offsets")
+    return out, cnt
+
+
+def token_segments(userid_bs):
+    rows, P = userid_bs.shape
+    s = torch.empty(rows * 2 * P, dtype=torch.int32, device=userid_bs.device)
+    e = torch.empty_like(s)
+    _check(load().graft_token_segments(ptr(userid_bs), rows, P, ptr(s), ptr(e), stream()), "graft_token_segments")
+    return s, e
+
+
+# ---------------------------------------------------------------- embedding --
+def item_gather(table, idx, x0):
+    _check(load().graft_item_gather(ptr(table), i64(table.shape[0]), table.shape[1], ptr(idx), i64(idx.numel()), ptr(x0),
+                                    stream()), "graft_item_gather")
+
+
+def action_embed(a: ActionArgs, x0, feats):
+    _check(load().graft_action_embed(C.byref(a), ptr(x0), ptr(feats), stream()), "graft_action_embed")
+
+
+def action_embed_bwd(a: ActionArgs, feats, dx0, dW, db, dg, ds, dst, dcos, dsin):
+    n, d = a.n, a.d
+    need = ((n + 255) // 256) * d * 33 * 4 + n * 32 * 4 + ((n + 127) // 128) * 256 * 4 + 4096
+    ws = scratch(need, dx0.device)
+    _check(load().graft_action_embed_bwd(C.byref(a), ptr(feats), ptr(dx0), ptr(dW), ptr(db), ptr(dg), ptr(ds), ptr(dst),
+                                         ptr(dcos), ptr(dsin), ptr(ws), i64(ws.numel()), stream()), "graft_action_embed_bwd")
+
+
+def scatter_add_sorted(g, g_stride, idx, d, grad_table):
+    n = idx.numel()
+    need = load().graft_scatter_add_scratch_bytes(i64(n), d)
+    ws = scratch(need, g.device)
+    _check(load().graft_scatter_add_sorted(ptr(g), i64(g_stride), ptr(idx), i64(n), d, ptr(grad_table),
+                                           i64(grad_table.shape[0]), ptr(ws), i64(ws.numel()), stream()),
+           "graft_scatter_add_sorted")
+
+
+# --------------------------------------------------------------------- GEMM --
+def gemm(A, B, Cout, M, N, K, *, a_kmajor=True, b_kmajor=True, lda=None, ldb=None, ldc=None, epilogue=EPI_BF16,
+         resid=None, ldr=None, bias=None, aux=None, ldaux=None, ce=None, n_offset=0, split_k=0):
+    """C[M,N] = op(A) op(B); see include/graft.h graft_gemm_args.  A/B/C may be
+    views: pass explicit leading dimensions."""
+    g = GemmArgs()
+    g.A, g.lda, g.a_kmajor = vp(A.data_ptr()), (lda if lda is not None else (K if a_kmajor else M)), int(a_kmajor)
+    g.B, g.ldb, g.b_kmajor = vp(B.data_ptr()), (ldb if ldb is not None else (K if b_kmajor else N)), int(b_kmajor)
+    g.C, g.ldc = (vp(Cout.data_ptr()) if Cout is not None else vp(1)), (ldc if ldc is not None else N)
+    g.M, g.N, g.K = M, N, K
+    g.epilogue = epilogue
+    if resid is not None:
+        g.resid, g.ldr = vp(resid.data_ptr()), (ldr if ldr is not None else N)
+    if bias is not None:
+        g.bias = vp(bias.data_ptr())
+    if aux is not None:
+        g.aux, g.ldaux = vp(aux.data_ptr()), (ldaux if ldaux is not None else N)
+    if ce is not None:
+        for k, v in ce.items():
+            setattr(g, "ce_" + k, vp(v.data_ptr()))
+    g.n_offset = n_offset
+    g.split_k = split_k
+    lib = load()
+    need = lib.graft_gemm_scratch_bytes(C.byref(g))
+    ws = scratch(need, A.device, slot=1) if need > 0 else None
+    _check(lib.graft_gemm_bf16(C.byref(g), ptr(ws), i64(ws.numel() if ws is not None else 0), stream()), "graft_gemm_bf16")
+
+
+def ce_nblocks(N):
+    return load().graft_gemm_ce_nblocks(i64(N))
+
+
+# ------------------------------------------------------------- element-wise --
+def rmsnorm_fwd(x, scale, y16, y32, rstd, eps=1e-5):
+    T, d = x.shape
+    _check(load().graft_rmsnorm_fwd(ptr(x), ptr(scale), ptr(y16), ptr(y32), ptr(rstd), i64(T), d, f32(eps), stream()),
+           "graft_rmsnorm_fwd")
+
+
+def rmsnorm_bwd(x, scale, rstd, dy16, dy32, dres, dx, dx16, dscale):
+    T, d = x.shape
+    ws = scratch(2 * max(device_sms(), 1) * d * 4 + 1024, x.device)
+    _check(load().graft_rmsnorm_bwd(ptr(x), ptr(scale), ptr(rstd), ptr(dy16), ptr(dy32), ptr(dres), ptr(dx), ptr(dx16),
+                                    ptr(dscale), i64(T), d, ptr(ws), i64(ws.numel()), stream()), "graft_rmsnorm_bwd")
+
+
+def rope(qkv, heads, row_len, cos, sin, pos=None, inverse=False):
+    T, ld = qkv.shape
+    _check(load().graft_rope(ptr(qkv), i64(T), i64(ld), heads, row_len, ptr(pos), ptr(cos), ptr(sin), int(inverse), stream()),
+           "graft_rope")
+
+
+def swiglu_fwd(gu, act):
+    T, I = act.shape
+    _check(load().graft_swiglu_fwd(ptr(gu), ptr(act), i64(T), I, stream()), "graft_swiglu_fwd")
+
+
+def swiglu_bwd(gu, dact, dgu):
+    T, I = dact.shape
+    _check(load().graft_swiglu_bwd(ptr(gu), ptr(dact), ptr(dgu), i64(T), I, stream()), "graft_swiglu_bwd")
+
+
+def cast_bf16(src, dst):
+    _check(load().graft_cast_f32_to_bf16(ptr(src), ptr(dst), i64(src.numel()), stream()), "graft_cast_f32_to_bf16")
+
+
+def cast_pad_rows(src, dst):
+    rows, cols = src.shape
+    _check(load().graft_cast_pad_rows(ptr(src), i64(rows), i64(cols), ptr(dst), i64(dst.shape[1]), stream()),
+           "graft_cast_pad_rows")
+
+
+def colsum(src, out):
+    rows, cols = src.shape
+    ws = scratch(256 * cols * 4, src.device)
+    f, b = (ptr(src), None) if src.dtype == torch.float32 else (None, ptr(src))
+    _check(load().graft_colsum(f, b, i64(rows), i64(cols), i64(cols), ptr(out), ptr(ws), i64(ws.numel()), stream()),
+           "graft_colsum")
+
+
+def axpy(y, x, alpha):
+    _check(load().graft_axpy_f32(ptr(y), ptr(x), f32(alpha), i64(y.numel()), stream()), "graft_axpy_f32")
+
+
+# ---------------------------------------------------------------- attention --
+def attn_args(qkv, H, G, rows, row_len, uid_tok, tm_tok, seg_s, seg_e):
+    a = AttnArgs()
+    a.qkv, a.ld, a.k_col, a.v_col = vp(qkv.data_ptr()), qkv.shape[1], H * 64, (H + G) * 64
+    a.H, a.G, a.rows, a.row_len = H, G, rows, row_len
+    a.userid_tok, a.tm_tok, a.seg_start, a.seg_end = ptr(uid_tok), ptr(tm_tok), ptr(seg_s), ptr(seg_e)
+    return a
+
+
+def attn_fwd(a: AttnArgs, out, lse2):
+    _check(load().graft_attn_fwd(C.byref(a), ptr(out), ptr(lse2), stream()), "graft_attn_fwd")
+
+
+def attn_bwd(a: AttnArgs, out, dout, lse2, dqkv, delta):
+    _check(load().graft_attn_bwd(C.byref(a), ptr(out), ptr(dout), ptr(lse2), ptr(dqkv), ptr(delta), stream()), "graft_attn_bwd")
+
+
+# -------------------------------------------------------------------- heads --
+def select_rows(weight, label, position, cap):
+    dev = weight.device
+    sel = torch.empty(cap, dtype=torch.int32, device=dev)
+    w = torch.empty(cap, dtype=torch.float32, device=dev)
+    lab = torch.empty(cap, dtype=torch.float32, device=dev)
+    pos = torch.empty(cap, dtype=torch.int32, device=dev)
+    cnt = torch.empty(1, dtype=torch.int32, device=dev)
+    _check(load().graft_select_rows(ptr(weight), ptr(label), ptr(position), i64(weight.numel()), cap, ptr(sel), ptr(w), ptr(lab),
+                                    ptr(pos), ptr(cnt), stream()), "graft_select_rows")
+    return sel, w, lab, pos, cnt
+
+
+def gather_rows_bf16(x, sel, parity, out):
+    _check(load().graft_gather_rows_bf16(ptr(x), x.shape[1], ptr(sel), sel.numel(), parity, ptr(out), stream()),
+           "graft_gather_rows_bf16")
+
+
+def scatter_rows_f32(g, sel, parity, dx):
+    _check(load().graft_scatter_rows_f32(ptr(g), g.shape[1], ptr(sel), sel.numel(), parity, ptr(dx), stream()),
+           "graft_scatter_rows_f32")
+
+
+def ce_finish(pmax, psum, n_blocks, tgt, lab, w, lse, coef, term, loss):
+    _check(load().graft_ce_finish(ptr(pmax), ptr(psum), n_blocks, ptr(tgt), tgt.numel(), ptr(lab), ptr(w), ptr(lse), ptr(coef),
+                                  ptr(term), ptr(loss), stream()), "graft_ce_finish")
+
+
+def rating_tail(h1, w2, b2, lab, w, mean, pred, loss4):
+    cap, d = h1.shape
+    _check(load().graft_rating_tail(ptr(h1), d, ptr(w2), ptr(b2), cap, ptr(lab), ptr(w), f32(mean), ptr(pred), ptr(loss4), stream()),
+           "graft_rating_tail")
+
+
+def rating_tail_bwd(pre, h1, w2, lab, w, mean, pred, loss4, gscale, dpre, dp, dw2, db2):
+    cap, d = h1.shape
+    _check(load().graft_rating_tail_bwd(ptr(pre), ptr(h1), d, ptr(w2), cap, ptr(lab), ptr(w), f32(mean), ptr(pred), ptr(loss4),
+                                        vp(gscale.data_ptr()), ptr(dpre), ptr(dp), ptr(dw2), ptr(db2), stream()),
+           "graft_rating_tail_bwd")
+
+
+def scale_by_scalar(v, scalar):
+    _check(load().graft_scale_by_scalar(ptr(v), vp(scalar.data_ptr()), i64(v.numel()), stream()), "graft_scale_by_scalar")
+
+
+def interleave_i32(a, out):
+    _check(load().graft_interleave_i32(ptr(a), i64(a.numel()), ptr(out), stream()), "graft_interleave_i32")
+
+
+# ---------------------------------------------------------------- optimiser --
+def adamw(p, g, m, v, lr, b1, b2, eps, wd, step, grad_scale=None):
+    _check(load().graft_adamw(ptr(p), ptr(g), ptr(m), ptr(v), i64(p.numel()), f32(lr), f32(b1), f32(b2), f32(eps), f32(wd),
+                              int(step), ptr(grad_scale), stream()), "graft_adamw")
+
+
+def sumsq(x, out_accum):
+    ws = scratch(4 * 4 * max(device_sms(), 1) + 64, x.device)
+    _check(load().graft_sumsq_f32(ptr(x), i64(x.numel()), ptr(out_accum), ptr(ws), i64(ws.numel()), stream()), "graft_sumsq_f32")

@@ -1,0 +1,528 @@
+"""Drop-in `RecommenderModel` whose train step runs on libgraft's sm_100a kernels.
+
+Mirrors the call surface of the reference module
+(/root/reference/notebooks/Training/transformer.model.py, cited as `ref:` below):
+  * names: ALL_MEDIUMS, ALL_METRICS, RecommenderModel(config)          ref:1-2,346
+  * model(d, evaluate) -> [0.watch, 0.rating, 1.watch, 1.rating]        ref:493-529
+    (rating entries are lists of 3 moments when evaluate=True);
+    `d` is reshaped and masked IN PLACE exactly as ref:495-497 does, because the
+    trainer reads d[...weight].sum() afterwards (transformer.py:261)
+  * identical parameter tree / state_dict keys / init                    ref:5-12,346-360
+  * load_pretrained_embeddings semantics                                 ref:379-389
+
+Host side is PyTorch for parameters, autograd plumbing and allocation only.
+Every contraction, gather, scatter, norm and loss of the step is a libgraft
+kernel reached through recommendersystem_b200.lib (ctypes over the C ABI).
+There is no fallback path: without CUDA + libgraft.so the forward raises.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import lib as L
+
+ALL_MEDIUMS = [0, 1]
+ALL_METRICS = ["watch", "rating"]
+
+
+def init_weights(module, std=0.006):
+    """ref:5-12."""
+    if isinstance(module, nn.Linear):
+        module.weight.data.normal_(mean=0.0, std=std)
+        if module.bias is not None:
+            module.bias.data.zero_()
+    elif isinstance(module, nn.Embedding):
+        module.weight.data.normal_(mean=0.0, std=std)
+        module.weight.data[-1].fill_(0)
+
+
+# ------------------------------------------------------------------------------
+# Parameter containers.  They carry the reference's module/parameter names so
+# that checkpoints interchange; none of them computes.
+# ------------------------------------------------------------------------------
+class MaskedEmbedding(nn.Module):
+    def __init__(self, vocab_size, embed_dim):
+        super().__init__()
+        self.vocab_size = vocab_size + 1  # last row = the "-1" (masked) row, ref:15-24
+        self.embedding = nn.Embedding(self.vocab_size, embed_dim)
+
+
+class ActionEmbedding(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.periodic_time_cos = nn.Parameter(torch.zeros(2))
+        self.periodic_time_sin = nn.Parameter(torch.zeros(2))
+        vs = config["vocab_sizes"]
+        self.status_embedding = MaskedEmbedding(vs["status"], 16)
+        self.gender_embedding = MaskedEmbedding(vs["gender"], 4)
+        self.source_embedding = MaskedEmbedding(vs["source"], 4)
+        self.linear = nn.Linear(32, config["embed_dim"])  # ref:36-49: 1+2+2+4+4+1+1+16+1 features
+
+
+class ItemEmbedding(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        vocab = sum(config["vocab_sizes"][f"{m}_matchedid"] for m in ALL_MEDIUMS)
+        self.vocab_size = vocab
+        self.matchedid_embedding = MaskedEmbedding(vocab, config["embed_dim"])
+        self.metadata_embedding = MaskedEmbedding(vocab, config["metadata_emb_size"])
+        for p in self.metadata_embedding.parameters():
+            p.requires_grad = False  # ref:113-114
+        self.projection_layer = nn.Linear(config["metadata_emb_size"], config["embed_dim"])
+
+
+class DualItemEmbedding(nn.Module):
+    """Weight-tied cloze head: registers the same ItemEmbedding again (ref:148-151,354),
+    which is why state_dict carries watch_head.item_embedding.* aliases."""
+
+    def __init__(self, item_embedding):
+        super().__init__()
+        self.item_embedding = item_embedding
+
+
+class RMSNorm(nn.Module):
+    def __init__(self, dim, eps=1e-5):
+        super().__init__()
+        self.eps = eps
+        self.scale = nn.Parameter(torch.ones(dim))
+
+
+class SwiGLU(nn.Module):
+    def __init__(self, dim, inter):
+        super().__init__()
+        self.w1 = nn.Linear(dim, inter, bias=False)
+        self.w2 = nn.Linear(inter, dim, bias=False)
+        self.w3 = nn.Linear(dim, inter, bias=False)
+
+
+class FlashAttention(nn.Module):  # name kept for state_dict/module-tree parity (ref:216)
+    def __init__(self, config):
+        super().__init__()
+        d, H, G = config["embed_dim"], config["num_heads"], config["num_kv_heads"]
+        hd = d // H
+        self.q_proj = nn.Linear(d, H * hd, bias=False)
+        self.k_proj = nn.Linear(d, G * hd, bias=False)
+        self.v_proj = nn.Linear(d, G * hd, bias=False)
+        self.output_proj = nn.Linear(H * hd, d, bias=False)
+
+
+class TransformerBlock(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.attn = FlashAttention(config)
+        self.mlp = SwiGLU(config["embed_dim"], config["intermediate_dim"])
+        self.sa_norm = RMSNorm(config["embed_dim"])
+        self.mlp_norm = RMSNorm(config["embed_dim"])
+
+
+class Transformer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.layers = nn.ModuleList([TransformerBlock(config) for _ in range(config["num_layers"])])
+        self.norm = RMSNorm(config["embed_dim"])
+        hd = config["embed_dim"] // config["num_heads"]
+        n = 2 * config["max_sequence_length"]  # item + action token per position, ref:321-322
+        inv = 1.0 / (500000.0 ** (torch.arange(0, hd, 2)[: hd // 2].float() / hd))  # ref:173-179
+        ang = torch.outer(torch.arange(n, dtype=torch.float32), inv)
+        self.register_buffer("freqs_cos", torch.cos(ang), persistent=False)
+        self.register_buffer("freqs_sin", torch.sin(ang), persistent=False)
+
+
+# ------------------------------------------------------------------------------
+class _Params:
+    """Flat, ordered view of the trainable tensors the step differentiates."""
+
+    def __init__(self, model):
+        ae, ie, tr = model.action_embedding, model.item_embedding, model.transformers
+        self.names, self.tensors = [], []
+
+        def add(n, t):
+            self.names.append(n)
+            self.tensors.append(t)
+
+        add("ae.cos", ae.periodic_time_cos); add("ae.sin", ae.periodic_time_sin)
+        add("ae.status", ae.status_embedding.embedding.weight)
+        add("ae.gender", ae.gender_embedding.embedding.weight)
+        add("ae.source", ae.source_embedding.embedding.weight)
+        add("ae.w", ae.linear.weight); add("ae.b", ae.linear.bias)
+        add("ie.id", ie.matchedid_embedding.embedding.weight)
+        add("ie.pw", ie.projection_layer.weight); add("ie.pb", ie.projection_layer.bias)
+        for i, l in enumerate(tr.layers):
+            add(f"l{i}.q", l.attn.q_proj.weight); add(f"l{i}.k", l.attn.k_proj.weight)
+            add(f"l{i}.v", l.attn.v_proj.weight); add(f"l{i}.o", l.attn.output_proj.weight)
+            add(f"l{i}.w1", l.mlp.w1.weight); add(f"l{i}.w2", l.mlp.w2.weight); add(f"l{i}.w3", l.mlp.w3.weight)
+            add(f"l{i}.san", l.sa_norm.scale); add(f"l{i}.mln", l.mlp_norm.scale)
+        add("norm", tr.norm.scale)
+        add("rh.w0", model.rating_head[0].weight); add("rh.b0", model.rating_head[0].bias)
+        add("rh.w2", model.rating_head[2].weight); add("rh.b2", model.rating_head[2].bias)
+        self.index = {n: i for i, n in enumerate(self.names)}
+
+
+def _bf16(shape, dev):
+    return torch.empty(shape, dtype=torch.bfloat16, device=dev)
+
+
+def _f32(shape, dev):
+    return torch.empty(shape, dtype=torch.float32, device=dev)
+
+
+class _ClozeStep(torch.autograd.Function):
+    """Whole step as one autograd node: forward returns the loss vector, backward
+    consumes d(loss vector) (a device tensor, no host sync) and returns every
+    parameter gradient.  All compute is libgraft kernels on the current stream."""
+
+    @staticmethod
+    def forward(ctx, model, d, evaluate, *params):
+        cfg = model.config
+        P = model._params
+        W = dict(zip(P.names, params))
+        dev = W["ie.id"].device
+        if dev.type != "cuda":
+            raise L.GraftError("the cloze step has no CPU path: move the model and batch to a CUDA device")
+        B, S = d["userid"].shape
+        N, T = B * S, 2 * B * S
+        dm, H, G, I = cfg["embed_dim"], cfg["num_heads"], cfg["num_kv_heads"], cfg["intermediate_dim"]
+        nl = cfg["num_layers"]
+        assert dm // H == 64, "libgraft attention is built for head_dim 64 (as the reference configs use)"
+        QKV = (H + 2 * G) * 64
+        V0 = cfg["vocab_sizes"]["0_matchedid"]
+        Vt = V0 + cfg["vocab_sizes"]["1_matchedid"]
+        sv = {}  # saved for backward
+
+        # ---- bf16 operand copies of the weights (autocast's casts, done once per step) ----
+        wq = []
+        for i in range(nl):
+            qkv_w = _bf16((QKV, dm), dev)
+            L.cast_bf16(W[f"l{i}.q"], qkv_w[: H * 64]); L.cast_bf16(W[f"l{i}.k"], qkv_w[H * 64:(H + G) * 64])
+            L.cast_bf16(W[f"l{i}.v"], qkv_w[(H + G) * 64:])
+            o_w = _bf16((dm, H * 64), dev); L.cast_bf16(W[f"l{i}.o"], o_w)
+            w13 = _bf16((2 * I, dm), dev); L.cast_bf16(W[f"l{i}.w1"], w13[:I]); L.cast_bf16(W[f"l{i}.w3"], w13[I:])
+            w2 = _bf16((dm, I), dev); L.cast_bf16(W[f"l{i}.w2"], w2)
+            wq.append((qkv_w, o_w, w13, w2))
+        sv["wq"] = wq
+
+        # ---- fused item table = id rows + bf16(meta . Wp^T + bp)   (ref:120-128 / 165-169) ----
+        meta16, Mp = model._meta_bf16()
+        pw16 = _bf16((dm, Mp), dev); L.cast_pad_rows(W["ie.pw"], pw16)
+        table = _f32((Vt + 1, dm), dev)
+        L.gemm(meta16, pw16, table, Vt + 1, dm, Mp, epilogue=L.EPI_TABLE, resid=W["ie.id"], bias=W["ie.pb"])
+        table16 = _bf16((Vt + 1, dm), dev); L.cast_bf16(table, table16)
+        sv["pw16"], sv["table16"] = pw16, table16
+
+        # ---- tokens: x0[2i] = table[id], x0[2i+1] = action Linear (ref:464-467) ----
+        x = _f32((T, dm), dev)
+        mid = d["matchedid"].reshape(-1)
+        L.item_gather(table, mid, x)
+        aa = model._action_args(d, W, N)
+        feats = _f32((N, 32), dev)
+        L.action_embed(aa, x, feats)
+        sv["feats"], sv["aa"], sv["mid"] = feats, aa, mid
+
+        uid_tok = torch.empty(T, dtype=torch.int32, device=dev); L.interleave_i32(d["userid"].reshape(-1), uid_tok)
+        tm_tok = torch.empty(T, dtype=torch.int32, device=dev); L.interleave_i32(d["token_mask_ids"].reshape(-1), tm_tok)
+        seg_s, seg_e = L.token_segments(d["userid"])
+        sv["seg"] = (uid_tok, tm_tok, seg_s, seg_e)
+        cos, sin = model.transformers.freqs_cos, model.transformers.freqs_sin
+
+        # ---- block stack (ref:297-343) ----
+        layers = []
+        for i in range(nl):
+            qkv_w, o_w, w13, w2 = wq[i]
+            xn = _bf16((T, dm), dev); r1 = _f32((T,), dev)
+            L.rmsnorm_fwd(x, W[f"l{i}.san"], xn, None, r1)
+            qkv = _bf16((T, QKV), dev)
+            L.gemm(xn, qkv_w, qkv, T, QKV, dm)
+            L.rope(qkv, H + G, 2 * S, cos, sin)
+            ao = _bf16((T, H * 64), dev); lse = _f32((H, T), dev)
+            at = L.attn_args(qkv, H, G, B, 2 * S, uid_tok, tm_tok, seg_s, seg_e)
+            L.attn_fwd(at, ao, lse)
+            h = _f32((T, dm), dev)
+            L.gemm(ao, o_w, h, T, dm, H * 64, epilogue=L.EPI_RESID, resid=x)
+            hn = _bf16((T, dm), dev); r2 = _f32((T,), dev)
+            L.rmsnorm_fwd(h, W[f"l{i}.mln"], hn, None, r2)
+            gu = _bf16((T, 2 * I), dev)
+            L.gemm(hn, w13, gu, T, 2 * I, dm)
+            act = _bf16((T, I), dev)
+            L.swiglu_fwd(gu, act)
+            xo = _f32((T, dm), dev)
+            L.gemm(act, w2, xo, T, dm, I, epilogue=L.EPI_RESID, resid=h)
+            layers.append((x, xn, r1, qkv, ao, lse, h, hn, r2, gu, act))
+            x = xo
+        hidden = _f32((T, dm), dev); rF = _f32((T,), dev)
+        L.rmsnorm_fwd(x, W["norm"], None, hidden, rF)
+        sv["layers"], sv["xL"], sv["rF"] = layers, x, rF
+        if model._taps is not None:
+            model._taps.update(x0=layers[0][0] if nl else x, hidden=hidden,
+                               **{f"layer{i}": (layers[i + 1][0] if i + 1 < nl else x) for i in range(nl)})
+
+        # ---- heads (ref:499-529) ----
+        cap = cfg["mask_topk"] * B
+        out = torch.zeros(16, dtype=torch.float32, device=dev)  # [4 losses | 2x4 rating moments(+den)]
+        w0_16 = _bf16((dm, dm), dev); L.cast_bf16(W["rh.w0"], w0_16)
+        sv["w0_16"] = w0_16
+        heads = []
+        for m in ALL_MEDIUMS:
+            lo, hi = (0, V0) if m == 0 else (V0, Vt)
+            K_m = hi - lo
+            # watch: fused logits + cross-entropy; [rows x catalog] never materialised
+            sel, ws, lab, pos, cnt = L.select_rows(d[f"{m}.watch.weight"].reshape(-1), d[f"{m}.watch.label"].reshape(-1),
+                                                   d[f"{m}.watch.position"].reshape(-1).to(torch.int32), cap)
+            hs = _bf16((cap, dm), dev); L.gather_rows_bf16(hidden, sel, 0, hs)
+            nb = L.ce_nblocks(K_m)
+            pmax = _f32((nb, cap), dev); psum = _f32((nb, cap), dev); tgt = torch.zeros(cap, dtype=torch.float32, device=dev)
+            L.gemm(hs, table16[lo:hi], None, cap, K_m, dm, epilogue=L.EPI_CE_PARTIAL,
+                   ce=dict(pmax=pmax, psum=psum, tgt=tgt, target=pos))
+            lse_r = _f32((cap,), dev); coef = _f32((cap,), dev); term = _f32((cap,), dev)
+            L.ce_finish(pmax, psum, nb, tgt, lab, ws, lse_r, coef, term, out[2 * m:2 * m + 1])
+            # rating: Linear -> GELU -> Linear(d,1), weighted MSE / moments
+            rsel, rws, rlab, _rpos, _rc = L.select_rows(d[f"{m}.rating.weight"].reshape(-1), d[f"{m}.rating.label"].reshape(-1),
+                                                        d[f"{m}.rating.position"].reshape(-1).to(torch.int32), cap)
+            rhs = _bf16((cap, dm), dev); L.gather_rows_bf16(hidden, rsel, 1, rhs)
+            h1 = _bf16((cap, dm), dev); pre = _bf16((cap, dm), dev)
+            L.gemm(rhs, w0_16, h1, cap, dm, dm, epilogue=L.EPI_BIAS_GELU, bias=W["rh.b0"], aux=pre)
+            pred = _f32((cap,), dev)
+            loss4 = out[4 + 4 * m: 8 + 4 * m]
+            L.rating_tail(h1, W["rh.w2"], W["rh.b2"], rlab, rws, cfg["rating_mean"], pred, loss4)
+            heads.append(dict(lo=lo, hi=hi, sel=sel, hs=hs, pos=pos, lse=lse_r, coef=coef, rsel=rsel, rhs=rhs, h1=h1, pre=pre,
+                              pred=pred, rlab=rlab, rws=rws))
+        out[1] = out[4]  # train MSE = first moment
+        out[3] = out[8]
+        sv["heads"], sv["out"] = heads, out
+        sv["dims"] = (B, S, N, T, dm, H, G, I, nl, QKV, V0, Vt, Mp, cap)
+        ctx.sv, ctx.model = sv, model
+        ctx.save_for_backward(*params)
+        ctx.set_materialize_grads(False)
+        res = out[:4].clone()
+        if evaluate:
+            mom = torch.stack((out[4:7], out[8:11])).clone()
+            ctx.mark_non_differentiable(mom)
+            return res, mom
+        return res
+
+    @staticmethod
+    def backward(ctx, gout, *unused):
+        sv, model = ctx.sv, ctx.model
+        cfg = model.config
+        P = model._params
+        params = ctx.saved_tensors
+        W = dict(zip(P.names, params))
+        B, S, N, T, dm, H, G, I, nl, QKV, V0, Vt, Mp, cap = sv["dims"]
+        dev = gout.device
+        gout = gout.contiguous().float()
+        G_ = {}  # name -> grad tensor
+
+        dtable = _f32((Vt + 1, dm), dev)
+        dtable[Vt].zero_()  # rows [0,Vt) are fully written by the head GEMMs below
+        dhid = torch.zeros((T, dm), dtype=torch.float32, device=dev)
+        table16 = sv["table16"]
+        CH = 4096
+        dw0 = _f32((dm, dm), dev); db0 = torch.zeros(dm, dtype=torch.float32, device=dev)
+        dw2 = torch.zeros(dm, dtype=torch.float32, device=dev); db2 = torch.zeros(1, dtype=torch.float32, device=dev)
+        tmp_dw2 = _f32((dm,), dev); tmp_db2 = _f32((1,), dev); tmp_db0 = _f32((dm,), dev)
+        for m, hd in enumerate(sv["heads"]):
+            lo, hi = hd["lo"], hd["hi"]
+            K_m = hi - lo
+            # ---- watch head backward: recompute logits chunk-wise, never store [rows x catalog] ----
+            coef = hd["coef"].clone(); L.scale_by_scalar(coef, gout[2 * m])
+            dhs = _f32((cap, dm), dev)
+            dlog = _bf16((cap, CH), dev)
+            for c0 in range(0, K_m, CH):
+                cn = min(CH, K_m - c0)
+                items = table16[lo + c0: lo + c0 + cn]
+                L.gemm(hd["hs"], items, dlog, cap, cn, dm, ldc=CH, epilogue=L.EPI_CE_GRAD,
+                       ce=dict(lse=hd["lse"], coef=coef, target=hd["pos"]), n_offset=c0)
+                # d hidden rows += dlogits . items
+                L.gemm(dlog, items, dhs, cap, dm, cn, lda=CH, b_kmajor=False, ldb=dm,
+                       epilogue=L.EPI_F32 if c0 == 0 else L.EPI_F32_ACCUM)
+                # d table rows = dlogits^T . hidden rows
+                L.gemm(dlog, hd["hs"], dtable[lo + c0: lo + c0 + cn], cn, dm, cap, a_kmajor=False, lda=CH, b_kmajor=False,
+                       ldb=dm, epilogue=L.EPI_F32, split_k=-1)
+            L.scatter_rows_f32(dhs, hd["sel"], 0, dhid)
+            # ---- rating head backward ----
+            dpre = _bf16((cap, dm), dev); dp = _f32((cap,), dev)
+            loss4 = sv["out"][4 + 4 * m: 8 + 4 * m]
+            L.rating_tail_bwd(hd["pre"], hd["h1"], W["rh.w2"], hd["rlab"], hd["rws"], cfg["rating_mean"], hd["pred"], loss4,
+                              gout[2 * m + 1], dpre, dp, tmp_dw2, tmp_db2)
+            dw2 += tmp_dw2; db2 += tmp_db2
+            L.gemm(dpre, hd["rhs"], dw0, dm, dm, cap, a_kmajor=False, lda=dm, b_kmajor=False, ldb=dm,
+                   epilogue=L.EPI_F32 if m == 0 else L.EPI_F32_ACCUM, split_k=-1)
+            L.colsum(dpre, tmp_db0); db0 += tmp_db0
+            drhs = _f32((cap, dm), dev)
+            L.gemm(dpre, sv["w0_16"], drhs, cap, dm, dm, b_kmajor=False, ldb=dm, epilogue=L.EPI_F32)
+            L.scatter_rows_f32(drhs, hd["rsel"], 1, dhid)
+        G_["rh.w0"], G_["rh.b0"], G_["rh.w2"], G_["rh.b2"] = dw0, db0, dw2.reshape(1, dm), db2
+
+        # ---- final norm ----
+        dx = _f32((T, dm), dev); dx16 = _bf16((T, dm), dev)
+        dn = _f32((dm,), dev)
+        L.rmsnorm_bwd(sv["xL"], W["norm"], sv["rF"], None, dhid, None, dx, dx16, dn)
+        G_["norm"] = dn
+        del dhid
+        uid_tok, tm_tok, seg_s, seg_e = sv["seg"]
+        cos, sin = model.transformers.freqs_cos, model.transformers.freqs_sin
+
+        for i in reversed(range(nl)):
+            x, xn, r1, qkv, ao, lse, h, hn, r2, gu, act = sv["layers"][i]
+            qkv_w, o_w, w13, w2 = sv["wq"][i]
+            # x_out = h + act . W2^T
+            dact = _bf16((T, I), dev)
+            L.gemm(dx16, w2, dact, T, I, dm, b_kmajor=False, ldb=I)
+            g_w2 = _f32((dm, I), dev)
+            L.gemm(dx16, act, g_w2, dm, I, T, a_kmajor=False, lda=dm, b_kmajor=False, ldb=I, epilogue=L.EPI_F32, split_k=-1)
+            dgu = _bf16((T, 2 * I), dev)
+            L.swiglu_bwd(gu, dact, dgu)
+            del dact
+            dhn = _bf16((T, dm), dev)
+            L.gemm(dgu, w13, dhn, T, dm, 2 * I, b_kmajor=False, ldb=dm)
+            g_w13 = _f32((2 * I, dm), dev)
+            L.gemm(dgu, hn, g_w13, 2 * I, dm, T, a_kmajor=False, lda=2 * I, b_kmajor=False, ldb=dm, epilogue=L.EPI_F32, split_k=-1)
+            del dgu
+            dh = _f32((T, dm), dev); dh16 = _bf16((T, dm), dev); g_mln = _f32((dm,), dev)
+            L.rmsnorm_bwd(h, W[f"l{i}.mln"], r2, dhn, None, dx, dh, dh16, g_mln)
+            # h = x + ao . Wo^T
+            dao = _bf16((T, H * 64), dev)
+            L.gemm(dh16, o_w, dao, T, H * 64, dm, b_kmajor=False, ldb=H * 64)
+            g_o = _f32((dm, H * 64), dev)
+            L.gemm(dh16, ao, g_o, dm, H * 64, T, a_kmajor=False, lda=dm, b_kmajor=False, ldb=H * 64, epilogue=L.EPI_F32, split_k=-1)
+            dqkv = _bf16((T, QKV), dev); delta = _f32((H, T), dev)
+            at = L.attn_args(qkv, H, G, B, 2 * S, uid_tok, tm_tok, seg_s, seg_e)
+            L.attn_bwd(at, ao, dao, lse, dqkv, delta)
+            L.rope(dqkv, H + G, 2 * S, cos, sin, inverse=True)
+            dxn = dhn  # reuse
+            L.gemm(dqkv, qkv_w, dxn, T, dm, QKV, b_kmajor=False, ldb=dm)
+            g_qkv = _f32((QKV, dm), dev)
+            L.gemm(dqkv, xn, g_qkv, QKV, dm, T, a_kmajor=False, lda=QKV, b_kmajor=False, ldb=dm, epilogue=L.EPI_F32, split_k=-1)
+            g_san = _f32((dm,), dev)
+            L.rmsnorm_bwd(x, W[f"l{i}.san"], r1, dxn, None, dh, dx, dx16, g_san)
+            G_[f"l{i}.q"], G_[f"l{i}.k"], G_[f"l{i}.v"] = g_qkv[: H * 64], g_qkv[H * 64:(H + G) * 64], g_qkv[(H + G) * 64:]
+            G_[f"l{i}.o"], G_[f"l{i}.w1"], G_[f"l{i}.w3"], G_[f"l{i}.w2"] = g_o, g_w13[:I], g_w13[I:], g_w2
+            G_[f"l{i}.san"], G_[f"l{i}.mln"] = g_san, g_mln
+            sv["layers"][i] = None  # free this layer's activations
+
+        # ---- token embeddings ----
+        L.scatter_add_sorted(dx, 2 * dm, sv["mid"], dm, dtable)  # item rows of the interleaved stream
+        ae = {k: torch.zeros_like(W[k]) for k in ("ae.w", "ae.b", "ae.gender", "ae.source", "ae.status", "ae.cos", "ae.sin")}
+        L.action_embed_bwd(sv["aa"], sv["feats"], dx, ae["ae.w"], ae["ae.b"], ae["ae.gender"], ae["ae.source"], ae["ae.status"],
+                           ae["ae.cos"], ae["ae.sin"])
+        G_.update(ae)
+        # fused table -> id rows, projection weight and bias (ref:139-145, 165-169)
+        G_["ie.id"] = dtable
+        dpb = _f32((dm,), dev); L.colsum(dtable, dpb)
+        G_["ie.pb"] = dpb
+        dt16 = _bf16((Vt + 1, dm), dev); L.cast_bf16(dtable, dt16)
+        meta16, _ = model._meta_bf16()
+        Mraw = cfg["metadata_emb_size"]
+        dpw = _f32((dm, Mraw), dev)
+        L.gemm(dt16, meta16, dpw, dm, Mraw, Vt + 1, a_kmajor=False, lda=dm, b_kmajor=False, ldb=Mp, epilogue=L.EPI_F32, split_k=-1)
+        G_["ie.pw"] = dpw
+        ctx.sv = None
+        grads = []
+        for n, needs in zip(P.names, ctx.needs_input_grad[3:]):
+            grads.append(G_[n].contiguous() if needs else None)
+        return (None, None, None, *grads)
+
+
+class RecommenderModel(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        if config.get("finetune"):
+            raise NotImplementedError("finetune/LoRA mode is not built yet (SURVEY.md 8f rank 4)")
+        self.action_embedding = ActionEmbedding(config)
+        self.item_embedding = ItemEmbedding(config)
+        self.transformers = Transformer(config)
+        self.watch_head = DualItemEmbedding(self.item_embedding)
+        self.rating_head = nn.Sequential(
+            nn.Linear(config["embed_dim"], config["embed_dim"]), nn.GELU(), nn.Linear(config["embed_dim"], 1))
+        self.apply(init_weights)
+        self._params = _Params(self)
+        self._meta_cache = None
+        self._taps = None
+        self.mask_rand = None  # tests may inject f(shape, device) -> randval
+        if config["forward"] == "train":
+            self.forward = self.train_forward
+        else:
+            raise NotImplementedError("inference forward is not built yet (SURVEY.md 8f rank 3)")
+
+    # ref:379-389, with the matrix passed in or read from <datadir>/media_embeddings.h5
+    def load_pretrained_embeddings(self, datadir=None, metadata=None):
+        if metadata is None:
+            import h5py  # same dependency as the reference
+            with h5py.File(f"{datadir}/media_embeddings.h5") as f:
+                metadata = f["metadata"][:]
+        w = self.item_embedding.metadata_embedding.embedding.weight
+        mt = torch.as_tensor(metadata, dtype=w.dtype, device=w.device)
+        assert mt.shape[0] + 1 == w.shape[0] and mt.shape[1] == w.shape[1]
+        with torch.no_grad():
+            w.zero_()
+            w[: mt.shape[0]].copy_(mt)
+        self._meta_cache = None
+
+    def _meta_bf16(self):
+        """bf16 copy of the frozen metadata table, rows padded to a 16-byte pitch for TMA."""
+        w = self.item_embedding.metadata_embedding.embedding.weight
+        key = (w.data_ptr(), w._version, str(w.device))
+        if self._meta_cache is None or self._meta_cache[0] != key:
+            Mp = (w.shape[1] + 7) // 8 * 8
+            buf = torch.empty((w.shape[0], Mp), dtype=torch.bfloat16, device=w.device)
+            L.cast_pad_rows(w.detach(), buf)
+            self._meta_cache = (key, buf, Mp)
+        return self._meta_cache[1], self._meta_cache[2]
+
+    def _action_args(self, d, W, N):
+        cfg = self.config
+        a = L.ActionArgs()
+        a.time, a.gender, a.source, a.status = L.ptr(d["time"]), L.ptr(d["gender"]), L.ptr(d["source"]), L.ptr(d["status"])
+        a.rating, a.progress = L.ptr(d["rating"]), L.ptr(d["progress"])
+        a.periodic_cos, a.periodic_sin = L.ptr(W["ae.cos"]), L.ptr(W["ae.sin"])
+        a.gender_table, a.source_table, a.status_table = L.ptr(W["ae.gender"]), L.ptr(W["ae.source"]), L.ptr(W["ae.status"])
+        a.gender_rows, a.source_rows, a.status_rows = W["ae.gender"].shape[0], W["ae.source"].shape[0], W["ae.status"].shape[0]
+        a.weight, a.bias = L.ptr(W["ae.w"]), L.ptr(W["ae.b"])
+        a.min_ts, a.max_ts = float(cfg["min_ts"]), float(cfg["max_ts"])
+        a.rating_mean, a.rating_std = float(cfg["rating_mean"]), float(cfg["rating_std"])
+        a.n, a.d, a.round_bf16 = N, cfg["embed_dim"], 1
+        return a
+
+    def mask_tokens(self, d):
+        """ref:417-462 (pre-train branch): same draws, same in-place edits of `d`."""
+        shape, dev = d["userid"].shape, d["userid"].device
+        randval = self.mask_rand(shape, dev) if self.mask_rand is not None else torch.rand(shape, device=dev)
+        rate = self.config["mask_rate"]
+        watch = randval < rate
+        rating = (randval >= rate) & (randval < 2 * rate)
+        either = watch | rating
+        not_watch, not_rating = ~watch, ~rating
+        d["token_mask_ids"] *= rating
+        for k in d:  # masked_fill_ = the reference's boolean index assignment without its host sync
+            if k.endswith(".position") or k.endswith(".label") or k.endswith(".weight"):
+                if "watch" in k:
+                    d[k].masked_fill_(not_watch, 0)
+                elif "rating" in k:
+                    d[k].masked_fill_(not_rating, 0)
+                elif "status" not in k:
+                    raise AssertionError(k)
+            elif k == "matchedid":
+                d[k].masked_fill_(watch, -1)
+            elif k == "status":
+                d[k].masked_fill_(either, -1)
+            elif k in ("rating", "progress"):
+                d[k].masked_fill_(either, 0)
+            elif k not in ("userid", "token_mask_ids", "time", "gender", "source"):
+                raise AssertionError(k)
+        return d
+
+    @torch.compiler.disable
+    def train_forward(self, d, evaluate):
+        S = self.config["max_sequence_length"]
+        for k in d:
+            d[k] = d[k].reshape(-1, S)  # ref:495-496 (mutates the caller's dict, as the trainer expects)
+        d = self.mask_tokens(d)
+        for k in d:
+            if not d[k].is_contiguous():
+                d[k] = d[k].contiguous()
+        res = _ClozeStep.apply(self, d, bool(evaluate), *self._params.tensors)
+        if evaluate:
+            res, mom = res
+            return [res[0], [mom[0, 0], mom[0, 1], mom[0, 2]], res[2], [mom[1, 0], mom[1, 1], mom[1, 2]]]
+        return [res[0], res[1], res[2], res[3]]

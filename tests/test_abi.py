@@ -1,0 +1,92 @@
+"""CPU-side checks: libgraft.so loads, exports every symbol include/graft.h
+declares, and the host packing entry points agree with the oracle.  No GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import cloze_oracle as oc
+from recommendersystem_b200 import lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    if not os.path.exists(L.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+
+
+def test_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "graft.h")).read()
+    names = sorted(set(re.findall(r"^(?:int|int64_t|const char\*)\s+(graft_\w+)\s*\(", hdr, flags=re.M)))
+    assert len(names) >= 35
+    lib = ctypes.CDLL(L.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.graft_version() >= 100
+
+
+def test_jagged_offsets_host_matches_oracle():
+    rng = np.random.default_rng(0)
+    for n_users in (0, 1, 5, 300):
+        lens = rng.integers(1, 40, n_users)
+        u = np.repeat(rng.permutation(n_users).astype(np.int32) + 1, lens)
+        u = np.concatenate([u, np.zeros(rng.integers(0, 9), np.int32)])
+        assert np.array_equal(L.jagged_offsets_host(u), oc.jagged_offsets(u))
+    u = np.array([4, 4, 2, 4, 4, 4], np.int32)  # a userid may recur non-contiguously: runs, not groups
+    assert L.jagged_offsets_host(u).tolist() == [0, 2, 3, 6]
+
+
+def test_block_permutation_and_concat_host():
+    rng = np.random.default_rng(1)
+    u = np.repeat(np.arange(1, 50, dtype=np.int32), rng.integers(1, 30, 49))
+    off = L.jagged_offsets_host(u)
+    order = rng.permutation(len(off) - 1)
+    assert np.array_equal(L.block_permutation_host(off, order), oc.block_permutation(off, order))
+    with pytest.raises(L.GraftError):
+        L.block_permutation_host(off, np.array([len(off) + 3] * (len(off) - 1)))
+    pieces = [rng.standard_normal(int(k)).astype(np.float32) for k in rng.integers(0, 20, 7)]
+    n = sum(len(p) for p in pieces)
+    total = n + (-n) % 64
+    got = L.concat_pad_host(pieces, total)
+    ref = oc.concat_pad([{"userid": p} for p in pieces], 64)["userid"]
+    assert np.array_equal(got, ref)
+
+
+def test_synthetic_pack_is_reference_layout():
+    from recommendersystem_b200 import synthetic
+    cfg, rows = synthetic.make_config("C1")
+    b = synthetic.make_batches(cfg, rows, 2, seed=3)
+    assert len(b) == 2 and sorted(b[0]) == sorted(synthetic.all_keys()) and len(b[0]) == 27
+    for k, v in b[0].items():
+        assert v.dtype == synthetic.key_dtype(k) and v.shape == (rows * cfg["max_sequence_length"],)
+    off = L.jagged_offsets_host(np.concatenate([b[0]["userid"], b[1]["userid"]]))
+    assert len(off) > 10
+    V0 = cfg["vocab_sizes"]["0_matchedid"]
+    m1 = b[0]["1.watch.weight"] > 0
+    assert np.array_equal(b[0]["1.watch.position"][m1], b[0]["matchedid"][m1] - V0)
+
+
+def test_no_cpu_fallback():
+    import torch
+    from recommendersystem_b200.model import RecommenderModel
+    from recommendersystem_b200 import synthetic
+    cfg, rows = synthetic.make_config("tiny")
+    model = RecommenderModel(cfg)
+    d = {k: torch.as_tensor(v) for k, v in synthetic.make_batches(cfg, rows, 1)[0].items()}
+    with pytest.raises(L.GraftError):
+        model(d, False)
+
+
+def test_state_dict_surface(golden):
+    from recommendersystem_b200.testing import model_from_params
+    model = model_from_params(golden["config"], golden["param"], "cpu")
+    keys = set(model.state_dict())
+    assert {k for k in keys if not k.startswith("watch_head.")} == set(golden["param"])
+    assert {"watch_head." + k for k in golden["param"] if k.startswith("item_embedding.")} <= keys
+    frozen = [n for n, p in model.named_parameters() if not p.requires_grad]
+    assert frozen == ["item_embedding.metadata_embedding.embedding.weight"]

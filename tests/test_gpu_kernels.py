@@ -1,0 +1,370 @@
+"""Kernel-level parity on the B200: every libgraft kernel, called through the C ABI
+(recommendersystem_b200.lib = ctypes), against plain PyTorch on the same inputs.
+Integer / copy work is bit-exact; bf16 tensor-core work within stated tolerances."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from recommendersystem_b200 import lib as L  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def rel_err(got, ref):
+    got, ref = got.float(), ref.float()
+    return float((got - ref).norm() / ref.norm().clamp_min(1e-20))
+
+
+def report(name, got, ref, tol):
+    e = rel_err(got, ref)
+    if not (e < tol):
+        diff = (got.float() - ref.float()).abs()
+        bad = diff > (tol * ref.float().abs().max())
+        idx = bad.nonzero()[:8].tolist()
+        print(f"[{name}] rel {e:.3e} tol {tol:.1e} bad {int(bad.sum())}/{bad.numel()} first {idx}")
+        if got.dim() == 2:
+            rows = bad.any(1).nonzero().flatten()[:16].tolist()
+            cols = bad.any(0).nonzero().flatten()[:16].tolist()
+            print(f"[{name}] bad rows {rows} bad cols {cols}")
+    assert e < tol, (name, e)
+
+
+def g_randn(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+# ----------------------------------------------------------------------- GEMM --
+@pytest.mark.parametrize("a_k,b_k", [(1, 1), (1, 0), (0, 1), (0, 0)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 256), (296, 200, 136), (1024, 768, 768), (384, 2112, 1000)])
+def test_gemm_layouts(a_k, b_k, M, N, K):
+    A = g_randn(M, K, seed=1).bfloat16()
+    B = g_randn(N, K, seed=2).bfloat16()
+    ref = A.float() @ B.float().t()
+    As = A.contiguous() if a_k else A.t().contiguous()   # [M,K] or [K,M]
+    Bs = B.contiguous() if b_k else B.t().contiguous()   # [N,K] or [K,N]
+    out = torch.full((M, N), float("nan"), device=DEV)
+    L.gemm(As, Bs, out, M, N, K, a_kmajor=bool(a_k), b_kmajor=bool(b_k), epilogue=L.EPI_F32)
+    torch.cuda.synchronize()
+    report(f"gemm a_k={a_k} b_k={b_k} {M}x{N}x{K}", out, ref, 1e-5)
+
+
+def test_gemm_splitk_and_accum():
+    M, N, K = 256, 384, 8192
+    A = g_randn(K, M, seed=3).bfloat16()
+    B = g_randn(K, N, seed=4).bfloat16()
+    ref = A.float().t() @ B.float()
+    out = torch.zeros(M, N, device=DEV)
+    L.gemm(A, B, out, M, N, K, a_kmajor=False, b_kmajor=False, epilogue=L.EPI_F32, split_k=-1)
+    report("splitk auto", out, ref, 1e-5)
+    out2 = torch.ones(M, N, device=DEV)
+    L.gemm(A, B, out2, M, N, K, a_kmajor=False, b_kmajor=False, epilogue=L.EPI_F32_ACCUM, split_k=4)
+    report("splitk accum", out2, ref + 1, 1e-5)
+    out3 = torch.ones(M, N, device=DEV)
+    L.gemm(A, B, out3, M, N, K, a_kmajor=False, b_kmajor=False, epilogue=L.EPI_F32_ACCUM)
+    report("accum", out3, ref + 1, 1e-5)
+    # bitwise reproducible
+    out4 = torch.zeros(M, N, device=DEV)
+    L.gemm(A, B, out4, M, N, K, a_kmajor=False, b_kmajor=False, epilogue=L.EPI_F32, split_k=-1)
+    assert torch.equal(out, out4)
+
+
+def test_gemm_epilogues():
+    M, N, K = 520, 264, 192
+    A = g_randn(M, K, seed=5).bfloat16()
+    B = g_randn(N, K, seed=6, scale=0.1).bfloat16()
+    acc = A.float() @ B.float().t()
+    o = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    L.gemm(A, B, o, M, N, K)
+    assert torch.equal(o, acc.bfloat16()) or rel_err(o, acc.bfloat16()) < 2e-3
+    res = g_randn(M, N, seed=7)
+    o = torch.empty(M, N, device=DEV)
+    L.gemm(A, B, o, M, N, K, epilogue=L.EPI_RESID, resid=res)
+    report("resid", o, res + acc.bfloat16().float(), 1e-3)
+    bias = g_randn(N, seed=8)
+    pre = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    o = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    L.gemm(A, B, o, M, N, K, epilogue=L.EPI_BIAS_GELU, bias=bias, aux=pre)
+    pre_ref = (acc + bias.bfloat16().float()).bfloat16()
+    report("bias pre", pre, pre_ref, 3e-3)
+    report("bias gelu", o, torch.nn.functional.gelu(pre_ref.float()).bfloat16(), 3e-3)
+    o = torch.empty(M, N, device=DEV)
+    L.gemm(A, B, o, M, N, K, epilogue=L.EPI_TABLE, resid=res, bias=bias)
+    report("table", o, res + pre_ref.float(), 1e-3)
+
+
+def test_gemm_fused_cross_entropy():
+    M, N, K = 200, 1000, 128   # rows, catalog, dim
+    h = g_randn(M, K, seed=9).bfloat16()
+    items = g_randn(N, K, seed=10, scale=0.3).bfloat16()
+    tgt_idx = torch.randint(0, N, (M,), generator=torch.Generator().manual_seed(1)).to(DEV).int()
+    label = torch.ones(M, device=DEV)
+    w = (torch.rand(M, generator=torch.Generator().manual_seed(2)) > 0.3).float().to(DEV)
+    logits = (h.float() @ items.float().t()).bfloat16().float()
+    ce = torch.nn.functional.cross_entropy(logits, tgt_idx.long(), reduction="none")
+    loss_ref = (ce * label * w).sum() / w.sum().clamp_min(1e-8)
+    nb = L.ce_nblocks(N)
+    pmax = torch.empty(nb, M, device=DEV); psum = torch.empty(nb, M, device=DEV); tgt = torch.zeros(M, device=DEV)
+    L.gemm(h, items, None, M, N, K, epilogue=L.EPI_CE_PARTIAL, ce=dict(pmax=pmax, psum=psum, tgt=tgt, target=tgt_idx))
+    lse = torch.empty(M, device=DEV); coef = torch.empty(M, device=DEV); term = torch.empty(M, device=DEV)
+    loss = torch.zeros(1, device=DEV)
+    L.ce_finish(pmax, psum, nb, tgt, label, w, lse, coef, term, loss)
+    report("lse", lse, torch.logsumexp(logits, 1), 1e-5)
+    assert abs(float(loss) - float(loss_ref)) < 1e-4 * abs(float(loss_ref)), (float(loss), float(loss_ref))
+    # backward chunk: dlogits = coef * (softmax - onehot)
+    c0, cn = 256, 512
+    dl = torch.empty(M, cn, device=DEV, dtype=torch.bfloat16)
+    L.gemm(h, items[c0:c0 + cn], dl, M, cn, K, epilogue=L.EPI_CE_GRAD, ce=dict(lse=lse, coef=coef, target=tgt_idx), n_offset=c0)
+    sm = torch.softmax(logits, 1)
+    sm[torch.arange(M), tgt_idx.long()] -= 1
+    ref = (coef[:, None] * sm)[:, c0:c0 + cn]
+    report("ce grad", dl, ref, 1e-2)
+
+
+# ------------------------------------------------------------------ attention --
+def make_attn_case(rows, row_len, H, G, seed, long_runs=False):
+    g = torch.Generator().manual_seed(seed)
+    P = row_len // 2
+    uid = torch.zeros(rows, P, dtype=torch.int32)
+    for r in range(rows):
+        p, u = 0, 1 + r * 1000
+        while p < P:
+            n = int(torch.randint(3, P if long_runs else 90, (1,), generator=g))
+            uid[r, p:p + n] = u if not (r == rows - 1 and p + n >= P and not long_runs) else 0
+            p += n; u += 1
+    tm = (torch.rand(rows, P, generator=g) < 0.15).int()
+    T = rows * row_len
+    qkv = (torch.randn(T, (H + 2 * G) * 64, generator=g) * 0.8).bfloat16()
+    return uid.to(DEV), tm.to(DEV), qkv.to(DEV)
+
+
+def attn_reference(qkv, uid, tm, rows, row_len, H, G):
+    T = rows * row_len
+    q = qkv[:, :H * 64].float().view(rows, row_len, H, 64).transpose(1, 2)
+    k = qkv[:, H * 64:(H + G) * 64].float().view(rows, row_len, G, 64).transpose(1, 2)
+    v = qkv[:, (H + G) * 64:].float().view(rows, row_len, G, 64).transpose(1, 2)
+    u = uid.repeat_interleave(2, 1); t = tm.repeat_interleave(2, 1)
+    vis = (u[:, :, None] == u[:, None, :]) & ((t[:, None, :] == 0) | (t[:, :, None] == t[:, None, :]))
+    k = k.repeat_interleave(H // G, 1); v = v.repeat_interleave(H // G, 1)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    s = s.masked_fill(~vis[:, None], float("-inf"))
+    p = torch.softmax(s, -1)
+    o = p @ v
+    return o.transpose(1, 2).reshape(T, H * 64), torch.logsumexp(s, -1)  # lse [rows,H,row_len]
+
+
+@pytest.mark.parametrize("rows,row_len,H,G,long_runs", [(2, 128, 2, 1, False), (3, 512, 4, 2, False), (2, 1024, 2, 2, True)])
+def test_attention_fwd_bwd(rows, row_len, H, G, long_runs):
+    uid, tm, qkv = make_attn_case(rows, row_len, H, G, seed=rows * 7 + H, long_runs=long_runs)
+    T = rows * row_len
+    uid_tok = torch.empty(T, dtype=torch.int32, device=DEV); L.interleave_i32(uid.reshape(-1), uid_tok)
+    tm_tok = torch.empty(T, dtype=torch.int32, device=DEV); L.interleave_i32(tm.reshape(-1), tm_tok)
+    seg_s, seg_e = L.token_segments(uid)
+    # segments: bit-exact against a python scan
+    u2 = uid.repeat_interleave(2, 1).cpu().numpy()
+    exp_s = np.zeros_like(u2); exp_e = np.zeros_like(u2)
+    for r in range(rows):
+        st = 0
+        for t in range(row_len + 1):
+            if t == row_len or u2[r, t] != u2[r, st]:
+                exp_s[r, st:t] = st; exp_e[r, st:t] = t; st = t
+    assert np.array_equal(seg_s.cpu().numpy().reshape(rows, row_len), exp_s)
+    assert np.array_equal(seg_e.cpu().numpy().reshape(rows, row_len), exp_e)
+
+    a = L.attn_args(qkv, H, G, rows, row_len, uid_tok, tm_tok, seg_s, seg_e)
+    out = torch.empty(T, H * 64, device=DEV, dtype=torch.bfloat16)
+    lse2 = torch.empty(H, T, device=DEV)
+    L.attn_fwd(a, out, lse2)
+    torch.cuda.synchronize()
+    q = qkv.clone().float().requires_grad_(True)
+    ref_o, ref_lse = attn_reference(q, uid, tm, rows, row_len, H, G)
+    report("attn out", out, ref_o, 1e-2)
+    lse_nat = (lse2 * 0.6931471805599453).view(H, rows, row_len).permute(1, 0, 2)
+    report("attn lse", lse_nat, ref_lse, 1e-4)
+
+    do = g_randn(T, H * 64, seed=11).bfloat16()
+    ref_o.backward(do.float())
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(H, T, device=DEV)
+    L.attn_bwd(a, out, do, lse2, dqkv, delta)
+    torch.cuda.synchronize()
+    report("attn dq", dqkv[:, :H * 64], q.grad[:, :H * 64], 2e-2)
+    report("attn dk", dqkv[:, H * 64:(H + G) * 64], q.grad[:, H * 64:(H + G) * 64], 2e-2)
+    report("attn dv", dqkv[:, (H + G) * 64:], q.grad[:, (H + G) * 64:], 2e-2)
+
+
+# ------------------------------------------------------------ embedding path --
+def test_item_gather_bit_exact():
+    V, d, n = 1000, 768, 5000
+    table = g_randn(V + 1, d, seed=12)
+    idx = torch.randint(-1, V, (n,), generator=torch.Generator().manual_seed(3)).int().to(DEV)
+    x0 = torch.zeros(2 * n, d, device=DEV)
+    L.item_gather(table, idx, x0)
+    ref = table[torch.where(idx == -1, V, idx).long()]
+    assert torch.equal(x0[0::2], ref)
+    assert torch.count_nonzero(x0[1::2]) == 0
+
+
+@pytest.mark.parametrize("n,d,V", [(4096, 128, 50), (65536, 768, 100000), (1000, 256, 7)])
+def test_scatter_add_sorted(n, d, V):
+    g = torch.Generator().manual_seed(n)
+    idx = torch.randint(0, V, (n,), generator=g).int()
+    idx[torch.rand(n, generator=g) < 0.1] = -1          # the mask row is the heaviest bucket
+    idx = idx.to(DEV)
+    dx = g_randn(2 * n, d, seed=13)
+    base = g_randn(V + 1, d, seed=14)
+    out = base.clone()
+    L.scatter_add_sorted(dx, 2 * d, idx, d, out)
+    ref = base.double().index_add(0, torch.where(idx == -1, V, idx).long(), dx[0::2].double())
+    report("scatter", out, ref, 2e-6)
+    out2 = base.clone()
+    L.scatter_add_sorted(dx, 2 * d, idx, d, out2)
+    assert torch.equal(out, out2), "scatter-add must be bitwise reproducible"
+
+
+def test_jagged_offsets_device_matches_host():
+    u = torch.tensor(np.repeat(np.arange(1, 400), np.random.default_rng(0).integers(1, 60, 399)), dtype=torch.int32)
+    off_h = L.jagged_offsets_host(u.numpy())
+    off_d, cnt = L.jagged_offsets(u.to(DEV))
+    n = int(cnt)
+    assert n + 1 == len(off_h) and np.array_equal(off_d[: n + 1].cpu().numpy(), off_h)
+
+
+def test_action_embed_fwd_bwd():
+    from oracle import cloze_oracle as oc
+    from recommendersystem_b200.model import RecommenderModel
+    from recommendersystem_b200.synthetic import make_batches, make_config
+    cfg, rows = make_config("C1")
+    torch.manual_seed(0)
+    model = RecommenderModel(cfg).to(DEV)
+    with torch.no_grad():
+        model.action_embedding.periodic_time_cos.add_(torch.tensor([0.3, -0.2], device=DEV))
+        model.action_embedding.periodic_time_sin.add_(torch.tensor([0.1, 0.4], device=DEV))
+        model.action_embedding.linear.bias.normal_(0, 0.05)
+    b = make_batches(cfg, rows, 1, seed=1)[0]
+    d = {k: torch.as_tensor(v).to(DEV) for k, v in b.items()}
+    d["status"][::7] = -1
+    W = dict(zip(model._params.names, model._params.tensors))
+    n, dm = d["userid"].numel(), cfg["embed_dim"]
+    aa = model._action_args(d, W, n)
+    x0 = torch.zeros(2 * n, dm, device=DEV); feats = torch.empty(n, 32, device=DEV)
+    L.action_embed(aa, x0, feats)
+    p = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    f_ref = oc.action_features(d, p, cfg)
+    report("action feats", feats, f_ref, 1e-5)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y_ref = torch.nn.functional.linear(f_ref, p["action_embedding.linear.weight"], p["action_embedding.linear.bias"])
+    report("action linear", x0[1::2], y_ref.float(), 4e-3)
+    dx0 = g_randn(2 * n, dm, seed=15)
+    y_ref.backward(dx0[1::2].bfloat16())
+    g = {k: torch.zeros_like(W[k]) for k in ("ae.w", "ae.b", "ae.gender", "ae.source", "ae.status", "ae.cos", "ae.sin")}
+    L.action_embed_bwd(aa, feats, dx0, g["ae.w"], g["ae.b"], g["ae.gender"], g["ae.source"], g["ae.status"], g["ae.cos"], g["ae.sin"])
+    pre = "action_embedding."
+    for mine, ref in (("ae.w", "linear.weight"), ("ae.b", "linear.bias"), ("ae.gender", "gender_embedding.embedding.weight"),
+                      ("ae.source", "source_embedding.embedding.weight"), ("ae.status", "status_embedding.embedding.weight"),
+                      ("ae.cos", "periodic_time_cos"), ("ae.sin", "periodic_time_sin")):
+        report(mine, g[mine], p[pre + ref].grad, 2e-2)
+
+
+# --------------------------------------------------------------- element-wise --
+@pytest.mark.parametrize("T,d", [(1000, 128), (4096, 768), (513, 2048)])
+def test_rmsnorm_fwd_bwd(T, d):
+    x = g_randn(T, d, seed=16).requires_grad_(True)
+    scale = (1 + 0.1 * g_randn(d, seed=17)).requires_grad_(True)
+    y16 = torch.empty(T, d, device=DEV, dtype=torch.bfloat16); y32 = torch.empty(T, d, device=DEV); rstd = torch.empty(T, device=DEV)
+    L.rmsnorm_fwd(x.detach(), scale.detach(), y16, y32, rstd)
+    ref = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * scale
+    report("rms y32", y32, ref, 1e-6)
+    report("rms y16", y16, ref.bfloat16(), 1e-3)
+    dy = g_randn(T, d, seed=18).bfloat16()
+    dres = g_randn(T, d, seed=19)
+    ref.backward(dy.float())
+    dx = torch.empty(T, d, device=DEV); dx16 = torch.empty(T, d, device=DEV, dtype=torch.bfloat16); ds = torch.empty(d, device=DEV)
+    L.rmsnorm_bwd(x.detach(), scale.detach(), rstd, dy, None, dres, dx, dx16, ds)
+    report("rms dx", dx, x.grad + dres, 1e-5)
+    report("rms dx16", dx16, (x.grad + dres).bfloat16(), 3e-3)
+    report("rms dscale", ds, scale.grad, 1e-4)
+    ds2 = torch.empty(d, device=DEV)
+    L.rmsnorm_bwd(x.detach(), scale.detach(), rstd, None, dy.float(), None, dx, None, ds2)
+    report("rms dx f32 path", dx, x.grad, 1e-5)
+    assert torch.equal(ds, ds2)
+
+
+def test_rope_matches_reference_and_inverts():
+    from oracle import cloze_oracle as oc
+    rows, row_len, heads = 2, 256, 3
+    T = rows * row_len
+    cos, sin = oc.rope_tables(64, row_len)
+    cos, sin = cos.to(DEV).contiguous(), sin.to(DEV).contiguous()
+    x = g_randn(T, heads * 64 + 64, seed=20).bfloat16()
+    y = x.clone()
+    L.rope(y, heads, row_len, cos, sin)
+    ref = oc.rope(x[:, :heads * 64].view(rows, row_len, heads, 64), cos, sin).reshape(T, heads * 64)
+    assert torch.equal(y[:, :heads * 64], ref), rel_err(y[:, :heads * 64], ref)
+    assert torch.equal(y[:, heads * 64:], x[:, heads * 64:])
+    L.rope(y, heads, row_len, cos, sin, inverse=True)
+    report("rope inverse", y, x, 1e-2)
+
+
+def test_swiglu_fwd_bwd():
+    T, I = 777, 2112
+    gu = g_randn(T, 2 * I, seed=21).bfloat16()
+    act = torch.empty(T, I, device=DEV, dtype=torch.bfloat16)
+    L.swiglu_fwd(gu, act)
+    g, u = gu[:, :I].clone().requires_grad_(True), gu[:, I:].clone().requires_grad_(True)
+    ref = torch.nn.functional.silu(g) * u
+    report("swiglu", act, ref, 4e-3)
+    dact = g_randn(T, I, seed=22).bfloat16()
+    ref.backward(dact)
+    dgu = torch.empty_like(gu)
+    L.swiglu_bwd(gu, dact, dgu)
+    report("swiglu dg", dgu[:, :I], g.grad, 1e-2)
+    report("swiglu du", dgu[:, I:], u.grad, 1e-2)
+
+
+def test_casts_colsum_select():
+    x = g_randn(300, 6148, seed=23)
+    o = torch.empty(300, 6152, device=DEV, dtype=torch.bfloat16)
+    L.cast_pad_rows(x, o)
+    assert torch.equal(o[:, :6148], x.bfloat16()) and torch.count_nonzero(o[:, 6148:]) == 0
+    y = torch.empty(300 * 6148, device=DEV, dtype=torch.bfloat16)
+    L.cast_bf16(x.reshape(-1), y)
+    assert torch.equal(y, x.reshape(-1).bfloat16())
+    cs = torch.empty(6148, device=DEV)
+    L.colsum(x, cs)
+    report("colsum", cs, x.double().sum(0), 1e-5)
+    w = (torch.rand(65536, generator=torch.Generator().manual_seed(4)) < 0.06).float().to(DEV) * 0.5
+    lab = g_randn(65536, seed=24); pos = torch.arange(65536, device=DEV, dtype=torch.int32)
+    sel, ws, ls, ps, cnt = L.select_rows(w, lab, pos, 8192)
+    nz = w.nonzero().flatten()
+    k = int(cnt)
+    assert k == nz.numel() and torch.equal(sel[:k].long(), nz) and torch.all(sel[k:] == -1)
+    assert torch.equal(ws[:k], w[nz]) and torch.equal(ls[:k], lab[nz]) and torch.equal(ps[:k].long(), nz) and torch.all(ws[k:] == 0)
+
+
+def test_rating_tail_and_adamw():
+    cap, d = 512, 256
+    h1 = g_randn(cap, d, seed=25).bfloat16(); pre = g_randn(cap, d, seed=26).bfloat16()
+    w2 = g_randn(1, d, seed=27, scale=0.05); b2 = g_randn(1, seed=28)
+    lab = 7.5 + g_randn(cap, seed=29); w = (torch.rand(cap, generator=torch.Generator().manual_seed(5)) < 0.5).float().to(DEV)
+    pred = torch.empty(cap, device=DEV); loss4 = torch.empty(4, device=DEV)
+    L.rating_tail(h1, w2, b2, lab, w, 7.6, pred, loss4)
+    pr = (h1.float() @ w2.bfloat16().float().t()).flatten() + b2.bfloat16().float()
+    pr = pr.bfloat16().float()
+    y = lab - 7.6
+    den = w.sum().clamp_min(1e-8)
+    ref = [((c * pr - y) ** 2 * w).sum() / den for c in (1, 0, -1)]
+    report("pred", pred, pr, 4e-3)
+    for i in range(3):
+        assert abs(float(loss4[i]) - float(ref[i])) < 2e-2 * abs(float(ref[i]))
+    # AdamW against torch
+    p = g_randn(10000, seed=30); g = g_randn(10000, seed=31)
+    tp = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([tp], lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1)
+    m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in (1, 2, 3):
+        tp.grad = g.clone(); opt.step()
+        L.adamw(p, g, m, v, 1e-3, 0.9, 0.95, 1e-8, 0.1, step)
+    report("adamw", p, tp.detach(), 1e-6)
