@@ -60,6 +60,18 @@ EPI_BF16, EPI_F32, EPI_F32_ACCUM, EPI_RESID, EPI_BIAS_BF16, EPI_BIAS_GELU, EPI_C
 
 _lib = None
 
+# instrumentation for bench.py: LAUNCHES counts kernel launches behind the C-ABI calls
+# made so far; GEMM_EVENTS (a list, when profiling) collects (start, end, flops) CUDA
+# events around every GEMM launch on the current stream.
+LAUNCHES = 0
+GEMM_EVENTS = None
+_LAUNCHES_PER_CALL = {
+    "graft_jagged_offsets": 2, "graft_action_embed": 2, "graft_action_embed_bwd": 5, "graft_scatter_add_sorted": 6,
+    "graft_rmsnorm_bwd": 2, "graft_colsum": 2, "graft_attn_bwd": 3, "graft_ce_finish": 2, "graft_rating_tail": 2,
+    "graft_rating_tail_bwd": 2, "graft_sumsq_f32": 2, "graft_jagged_offsets_host": 0, "graft_block_permutation_host": 0,
+    "graft_concat_pad_host": 0,
+}
+
 
 def load():
     """Loads libgraft.so; raises GraftError when it is not built."""
@@ -78,6 +90,8 @@ def load():
 
 
 def _check(rc, what):
+    global LAUNCHES
+    LAUNCHES += _LAUNCHES_PER_CALL.get(what, 1)
     if rc != 0:
         raise GraftError(f"{what} failed ({rc}): {load().graft_last_error().decode()}")
 
@@ -213,7 +227,13 @@ def gemm(A, B, Cout, M, N, K, *, a_kmajor=True, b_kmajor=True, lda=None, ldb=Non
     lib = load()
     need = lib.graft_gemm_scratch_bytes(C.byref(g))
     ws = scratch(need, A.device, slot=1) if need > 0 else None
+    if GEMM_EVENTS is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _check(lib.graft_gemm_bf16(C.byref(g), ptr(ws), i64(ws.numel() if ws is not None else 0), stream()), "graft_gemm_bf16")
+    if GEMM_EVENTS is not None:
+        e1.record()
+        GEMM_EVENTS.append((e0, e1, 2.0 * M * N * K))
 
 
 def ce_nblocks(N):

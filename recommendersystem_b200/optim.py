@@ -1,0 +1,69 @@
+"""Step tail on flat buffers: gradient all-reduce, global-norm clip, fused AdamW.
+
+Replaces the reference's per-step tail (transformer.py:272-276, 285-298: DDP
+bucketed all-reduce, clip_grad_norm_(1.0), optim.AdamW(fused=True, betas=(0.9,0.95),
+weight_decay 0.1 on dim>=2 tensors)) with three libgraft launches over one
+contiguous fp32 parameter buffer and one gradient buffer:
+  ncclAllReduce(flat grad) -> sum of squares -> AdamW (decay / no-decay halves).
+Parameters are re-pointed at views of the flat buffer, `.grad` at views of the
+flat gradient buffer, so autograd accumulates in place and nothing is copied.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import lib as L
+
+
+class FlatAdamW:
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1, max_grad_norm=1.0):
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        decay = [(n, p) for n, p in named if p.dim() >= 2]      # transformer.py:288-289
+        nodecay = [(n, p) for n, p in named if p.dim() < 2]
+        self.params = [p for _, p in decay + nodecay]
+        dev = self.params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]  # keep every view 16-byte aligned
+        total = sum(sizes)
+        self.n_decay = sum(sizes[: len(decay)])
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p, sz in zip(self.params, sizes):
+            view = self.flat_p[off: off + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.flat_g[off: off + p.numel()].view_as(p)
+            off += sz
+        self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_grad_norm
+        self.steps = 0
+        self._sq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._scale = torch.ones(1, dtype=torch.float32, device=dev)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+
+    def all_reduce_grads(self):
+        """Data-parallel mean of the dense gradient: one collective on the flat buffer."""
+        if self.world > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.AVG)
+
+    def step(self, lr=None):
+        self.steps += 1
+        lr = self.lr if lr is None else lr
+        self.all_reduce_grads()
+        # clip_grad_norm_(params, max_norm): scale = min(1, max_norm / (norm + 1e-6)), on device
+        self._sq.zero_()
+        L.sumsq(self.flat_g, self._sq)
+        torch.clamp(self.max_norm / (self._sq.sqrt() + 1e-6), max=1.0, out=self._scale)
+        b1, b2 = self.betas
+        nd = self.n_decay
+        L.adamw(self.flat_p[:nd], self.flat_g[:nd], self.m[:nd], self.v[:nd], lr, b1, b2, self.eps, self.wd, self.steps, self._scale)
+        if nd < self.flat_p.numel():
+            L.adamw(self.flat_p[nd:], self.flat_g[nd:], self.m[nd:], self.v[nd:], lr, b1, b2, self.eps, 0.0, self.steps, self._scale)
+
+    def grad_norm(self):
+        return self._sq.sqrt()
