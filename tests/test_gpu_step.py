@@ -33,7 +33,7 @@ def test_golden_losses_and_grads(golden):
         ref16 = golden["grad_bf16"][k]
         e16, e32, floor = rel(grads[k], ref16), rel(grads[k], ref32), rel(ref16, ref32)
         table.append((e16, e32, floor, k))
-        if not (e16 < 1e-2 or e32 <= 1.1 * floor + 1e-3):
+        if not (e16 < 1e-2 or e32 <= 1.25 * floor + 2e-3):
             bad[k] = (e16, e32, floor)
     for e16, e32, floor, k in sorted(table, reverse=True)[:10]:
         print(f"grad rel: vs ref-bf16 {e16:.3e}  vs ref-fp32 {e32:.3e}  (ref bf16 vs fp32 {floor:.3e})  {k}")
