@@ -137,7 +137,7 @@ int graft_gemm_ce_nblocks(int64_t N);
 int graft_rmsnorm_fwd(const float* x, const float* scale, void* y_bf16, float* y_f32, float* rstd, int64_t T, int d,
                       float eps, graft_stream_t stream);
 /* dx = dres + rmsnorm_bwd(dy), optional bf16 copy of dx for the next GEMM;
- * dscale[d] overwritten (deterministic 2-pass); scratch >= 2*SMs*d*4 bytes */
+ * dscale[d] overwritten (deterministic 2-pass); scratch >= 4*SMs*d*4 bytes */
 int graft_rmsnorm_bwd(const float* x, const float* scale, const float* rstd, const void* dy_bf16, const float* dy_f32,
                       const float* dres, float* dx, void* dx_bf16, float* dscale, int64_t T, int d, void* scratch,
                       int64_t scratch_bytes, graft_stream_t stream);
@@ -166,13 +166,15 @@ int graft_axpy_f32(float* y, const float* x, float alpha, int64_t n, graft_strea
  * Softmax attention over jagged user segments, transformer.model.py:256-286 +
  * the visibility rule :479-487, GQA, head_dim 64, scale 1/8.  qkv is the fused
  * projection output [T, ld] bf16: q heads at column 0, k heads at k_col, v
- * heads at v_col.  Query t sees key s iff same row, userid equal (segment
- * bounds give the candidate range) and (tm[s]==0 or tm[t]==tm[s]).
- * out [T, H*64] bf16, lse [H, T] fp32 (natural log). */
+ * heads at v_col.  Query t sees key s iff s lies in t's userid run
+ * [seg_start[t], seg_end[t]) (graft_token_segments) and (tm[s]==0 or
+ * tm[t]==tm[s]).  Runs equal the reference's userid equality when no userid
+ * recurs non-contiguously inside a row: graft_check_rows counts violations.
+ * out [T, H*64] bf16, lse2 [H, T] fp32 = log2 of the softmax denominator incl. max. */
+int graft_check_rows(const int32_t* userid, int rows, int positions_per_row, int32_t* bad_count, graft_stream_t stream);
 typedef struct {
   const void* qkv; int64_t ld; int k_col; int v_col;
   int H; int G; int rows; int row_len;
-  const int32_t* userid_tok;   /* [T] userid per token */
   const int32_t* tm_tok;       /* [T] token_mask_ids per token */
   const int32_t* seg_start; const int32_t* seg_end; /* [T] */
 } graft_attn_args;

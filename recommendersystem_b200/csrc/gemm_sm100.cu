@@ -14,7 +14,7 @@ namespace graft {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps (two per TMEM lane quarter)
 constexpr int GROUP_M = 16;  // m-blocks per raster group: the A band stays L2-resident
 
 struct GemmDev {
@@ -189,7 +189,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], 256);
     }
     fence_barrier_init();
   }
@@ -265,7 +265,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------- epilogue ----
-    const int q = warp & 3;
+    const int q = warp & 3;              // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;    // which half of the tile's columns it handles
+    constexpr int CH = BN / 64;          // 32-column chunks per half
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int m_blk, n_blk, split;
@@ -286,7 +288,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float tgt_logit = 0.f;
         bool has_tgt = false;
         uint32_t r[32];
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half * CH; c < (half + 1) * CH; ++c) {
           tmem_ld_32x32(t_addr + c * 32, r);
           tmem_ld_wait();
 #pragma unroll
@@ -300,7 +302,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         float sum = 0.f;
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half * CH; c < (half + 1) * CH; ++c) {
           tmem_ld_32x32(t_addr + c * 32, r);
           tmem_ld_wait();
 #pragma unroll
@@ -309,14 +311,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (col < p.N) sum += __expf(bf16_round(__uint_as_float(r[j])) - mx);
           }
         }
-        if (row_ok) {
-          p.ce_pmax[(long long)n_blk * p.M + row] = mx;
-          p.ce_psum[(long long)n_blk * p.M + row] = sum;
+        if (row_ok) {  // one partial per (n-block, column half); an empty half leaves (-inf, 0)
+          p.ce_pmax[((long long)n_blk * 2 + half) * p.M + row] = mx;
+          p.ce_psum[((long long)n_blk * 2 + half) * p.M + row] = sum;
           if (has_tgt) p.ce_tgt[row] = tgt_logit;
         }
       } else {
         uint32_t r[32];
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half * CH; c < (half + 1) * CH; ++c) {
           tmem_ld_32x32(t_addr + c * 32, r);
           tmem_ld_wait();
           epilogue_chunk<BN>(p, r, row, n0 + c * 32, row_ok, split);
@@ -399,7 +401,8 @@ static int pick_split(const graft_gemm_args* g, int bn) {
 
 using namespace graft;
 
-extern "C" int graft_gemm_ce_nblocks(int64_t N) { return (int)((N + 255) / 256); }
+// rows of the CE partial buffers: two column halves per 256-wide n-block
+extern "C" int graft_gemm_ce_nblocks(int64_t N) { return 2 * (int)((N + 255) / 256); }
 
 extern "C" int64_t graft_gemm_scratch_bytes(const graft_gemm_args* g) {
   int bn = pick_bn(g);

@@ -52,7 +52,7 @@ class AttnArgs(C.Structure):
     _fields_ = [
         ("qkv", vp), ("ld", i64), ("k_col", C.c_int), ("v_col", C.c_int),
         ("H", C.c_int), ("G", C.c_int), ("rows", C.c_int), ("row_len", C.c_int),
-        ("userid_tok", vp), ("tm_tok", vp), ("seg_start", vp), ("seg_end", vp),
+        ("tm_tok", vp), ("seg_start", vp), ("seg_end", vp),
     ]
 
 
@@ -249,7 +249,7 @@ def rmsnorm_fwd(x, scale, y16, y32, rstd, eps=1e-5):
 
 def rmsnorm_bwd(x, scale, rstd, dy16, dy32, dres, dx, dx16, dscale):
     T, d = x.shape
-    ws = scratch(2 * max(device_sms(), 1) * d * 4 + 1024, x.device)
+    ws = scratch(4 * max(device_sms(), 1) * d * 4 + 1024, x.device)
     _check(load().graft_rmsnorm_bwd(ptr(x), ptr(scale), ptr(rstd), ptr(dy16), ptr(dy32), ptr(dres), ptr(dx), ptr(dx16),
                                     ptr(dscale), i64(T), d, ptr(ws), i64(ws.numel()), stream()), "graft_rmsnorm_bwd")
 
@@ -293,11 +293,19 @@ def axpy(y, x, alpha):
 
 
 # ---------------------------------------------------------------- attention --
-def attn_args(qkv, H, G, rows, row_len, uid_tok, tm_tok, seg_s, seg_e):
+def check_rows(userid_bs):
+    """Number of userid runs that repeat an earlier run's id inside a row (must be 0)."""
+    rows, P = userid_bs.shape
+    bad = torch.zeros(1, dtype=torch.int32, device=userid_bs.device)
+    _check(load().graft_check_rows(ptr(userid_bs), rows, P, ptr(bad), stream()), "graft_check_rows")
+    return bad
+
+
+def attn_args(qkv, H, G, rows, row_len, tm_tok, seg_s, seg_e):
     a = AttnArgs()
     a.qkv, a.ld, a.k_col, a.v_col = vp(qkv.data_ptr()), qkv.shape[1], H * 64, (H + G) * 64
     a.H, a.G, a.rows, a.row_len = H, G, rows, row_len
-    a.userid_tok, a.tm_tok, a.seg_start, a.seg_end = ptr(uid_tok), ptr(tm_tok), ptr(seg_s), ptr(seg_e)
+    a.tm_tok, a.seg_start, a.seg_end = ptr(tm_tok), ptr(seg_s), ptr(seg_e)
     return a
 
 

@@ -219,10 +219,9 @@ class _ClozeStep(torch.autograd.Function):
         L.action_embed(aa, x, feats)
         sv["feats"], sv["aa"], sv["mid"] = feats, aa, mid
 
-        uid_tok = torch.empty(T, dtype=torch.int32, device=dev); L.interleave_i32(d["userid"].reshape(-1), uid_tok)
         tm_tok = torch.empty(T, dtype=torch.int32, device=dev); L.interleave_i32(d["token_mask_ids"].reshape(-1), tm_tok)
         seg_s, seg_e = L.token_segments(d["userid"])
-        sv["seg"] = (uid_tok, tm_tok, seg_s, seg_e)
+        sv["seg"] = (tm_tok, seg_s, seg_e)
         cos, sin = model.transformers.freqs_cos, model.transformers.freqs_sin
 
         # ---- block stack (ref:297-343) ----
@@ -235,7 +234,7 @@ class _ClozeStep(torch.autograd.Function):
             L.gemm(xn, qkv_w, qkv, T, QKV, dm)
             L.rope(qkv, H + G, 2 * S, cos, sin)
             ao = _bf16((T, H * 64), dev); lse = _f32((H, T), dev)
-            at = L.attn_args(qkv, H, G, B, 2 * S, uid_tok, tm_tok, seg_s, seg_e)
+            at = L.attn_args(qkv, H, G, B, 2 * S, tm_tok, seg_s, seg_e)
             L.attn_fwd(at, ao, lse)
             h = _f32((T, dm), dev)
             L.gemm(ao, o_w, h, T, dm, H * 64, epilogue=L.EPI_RESID, resid=x)
@@ -359,7 +358,7 @@ class _ClozeStep(torch.autograd.Function):
         L.rmsnorm_bwd(sv["xL"], W["norm"], sv["rF"], None, dhid, None, dx, dx16, dn)
         G_["norm"] = dn
         del dhid
-        uid_tok, tm_tok, seg_s, seg_e = sv["seg"]
+        tm_tok, seg_s, seg_e = sv["seg"]
         cos, sin = model.transformers.freqs_cos, model.transformers.freqs_sin
 
         for i in reversed(range(nl)):
@@ -386,7 +385,7 @@ class _ClozeStep(torch.autograd.Function):
             g_o = _f32((dm, H * 64), dev)
             L.gemm(dh16, ao, g_o, dm, H * 64, T, a_kmajor=False, lda=dm, b_kmajor=False, ldb=H * 64, epilogue=L.EPI_F32, split_k=-1)
             dqkv = _bf16((T, QKV), dev); delta = _f32((H, T), dev)
-            at = L.attn_args(qkv, H, G, B, 2 * S, uid_tok, tm_tok, seg_s, seg_e)
+            at = L.attn_args(qkv, H, G, B, 2 * S, tm_tok, seg_s, seg_e)
             L.attn_bwd(at, ao, dao, lse, dqkv, delta)
             L.rope(dqkv, H + G, 2 * S, cos, sin, inverse=True)
             dxn = dhn  # reuse

@@ -135,6 +135,8 @@ def make_attn_case(rows, row_len, H, G, seed, long_runs=False):
             uid[r, p:p + n] = u if not (r == rows - 1 and p + n >= P and not long_runs) else 0
             p += n; u += 1
     tm = (torch.rand(rows, P, generator=g) < 0.15).int()
+    if long_runs:  # inference-style mask ids: several distinct non-zero ids (embed.py:122-125)
+        tm = tm * torch.randint(1, 5, (rows, P), generator=g).int()
     T = rows * row_len
     qkv = (torch.randn(T, (H + 2 * G) * 64, generator=g) * 0.8).bfloat16()
     return uid.to(DEV), tm.to(DEV), qkv.to(DEV)
@@ -159,7 +161,6 @@ def attn_reference(qkv, uid, tm, rows, row_len, H, G):
 def test_attention_fwd_bwd(rows, row_len, H, G, long_runs):
     uid, tm, qkv = make_attn_case(rows, row_len, H, G, seed=rows * 7 + H, long_runs=long_runs)
     T = rows * row_len
-    uid_tok = torch.empty(T, dtype=torch.int32, device=DEV); L.interleave_i32(uid.reshape(-1), uid_tok)
     tm_tok = torch.empty(T, dtype=torch.int32, device=DEV); L.interleave_i32(tm.reshape(-1), tm_tok)
     seg_s, seg_e = L.token_segments(uid)
     # segments: bit-exact against a python scan
@@ -173,7 +174,8 @@ def test_attention_fwd_bwd(rows, row_len, H, G, long_runs):
     assert np.array_equal(seg_s.cpu().numpy().reshape(rows, row_len), exp_s)
     assert np.array_equal(seg_e.cpu().numpy().reshape(rows, row_len), exp_e)
 
-    a = L.attn_args(qkv, H, G, rows, row_len, uid_tok, tm_tok, seg_s, seg_e)
+    assert int(L.check_rows(uid)) == 0
+    a = L.attn_args(qkv, H, G, rows, row_len, tm_tok, seg_s, seg_e)
     out = torch.empty(T, H * 64, device=DEV, dtype=torch.bfloat16)
     lse2 = torch.empty(H, T, device=DEV)
     L.attn_fwd(a, out, lse2)

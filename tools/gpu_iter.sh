@@ -1,0 +1,10 @@
+#!/bin/bash
+# quick iteration: kernel + step tests, then the bench line and a launch list
+mkdir -p gpurun_out
+bash tools/gpu_check.sh > gpurun_out/check.txt 2>&1; grep -E "^==|FAILED|rel " gpurun_out/check.txt | head -40
+timeout 900 python bench.py --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "== bench exit $?"; cat gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err
+B="python bench.py --steps 1 --warmup 0 --no-cpu-baseline"
+timeout 600 $B > gpurun_out/plain.log 2>&1 &&
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/ncu1.log 2>&1
+echo "== launches exit $?"
