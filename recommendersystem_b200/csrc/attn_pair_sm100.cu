@@ -1,36 +1,44 @@
 // Jagged softmax attention, GQA-pair kernels for sm_100a (head_dim 64).
 //
-// Two query heads that share one K/V head run in one CTA: warps 0-3 and 4-7 are two
-// softmax warpgroups (thread = accumulator row = TMEM lane), warp 8 is a dedicated
-// issue warp (TMA loads + tcgen05.mma, one thread).  K/V tiles are loaded once for
-// both heads; while one warpgroup does exp2/pack on its S tile the tensor pipe runs
-// the other head's MMAs, and the next S tile of a head is issued right behind its PV,
-// so neither side waits on the other.  Everything is mbarrier-driven:
+// Two query heads that share one K/V head run in one CTA of 17 warps:
+//   warps 0-15 : softmax/elementwise.  warp w -> head (w>>3), column half ((w>>2)&1),
+//                TMEM lane quarter (w&3).  A thread owns one accumulator row (TMEM lane)
+//                and one half of the tile's columns, so a head's 128x128 (or 128x64) tile
+//                is spread over 8 warps and every scheduler has 4 warps to hide latency.
+//   warp 16    : issue warp, one thread: TMA loads + tcgen05.mma.
+// K/V tiles are loaded once for both heads; while one head's warps do exp2/pack the
+// tensor pipe runs the other head's MMAs; a head's next S tile is issued right behind
+// its PV, and the O update of tile j is deferred until after the row max of tile j+1
+// so nobody waits on a just-issued MMA.  mbarrier protocol per head h:
 //   bar_s[h]  : tcgen05.commit -> S_h (and dP_h) of the current tile is in TMEM
-//   bar_p[h]  : 128 arrivals   -> P_h/dS_h is in smem, S_h has been read
+//   bar_p[h]  : 256 arrivals   -> P_h/dS_h is in smem, S_h has been read
 //   bar_pv[h] : tcgen05.commit -> the MMAs that read P_h/dS_h retired
 // Visibility handling (run ranges + ballot words) is the same as attn_sm100.cu.
 #include "attn_common.cuh"
 
 namespace graft {
 
-constexpr int PAIR_THREADS = 288;
+constexpr int PAIR_THREADS = 544;
+
+__device__ __forceinline__ void head_sync(int h) { asm volatile("bar.sync %0, 256;" ::"r"(h + 1) : "memory"); }
 
 // ================================================================ forward =====
-// smem: Q 2x16K | K 2x16K | V 2x16K | P 2x32K | mask ids [2 wg][2 st][128] | Z [2][2][4] | barriers
-constexpr int FP_SMEM = 32768 * 3 + 65536 + 2 * 2 * 128 * 4 + 2 * 2 * 4 * 4 + 256 + 1024;
+// smem: Q 2x16K | K 2x16K | V 2x16K | P 2x32K | mask ids [2 h][2 st][128] | Z [2][2][4] |
+//       row max exchange [2 h][2 half][128] | barriers
+constexpr int FP_SMEM = 32768 * 3 + 65536 + 2 * 2 * 128 * 4 + 2 * 2 * 4 * 4 + 2 * 2 * 128 * 4 + 256 + 1024;
 
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = smem_align1024(smem_raw);
   uint8_t* sQ = base;                 // [2 heads][16K]
   uint8_t* sK = sQ + 32768;           // [2 stages][16K]
   uint8_t* sV = sK + 32768;           // [2 stages][16K]
   uint8_t* sP = sV + 32768;           // [2 heads][32K]
-  int32_t* sT = reinterpret_cast<int32_t*>(sP + 65536);  // [2 wg][2 st][128]
-  uint32_t* sZ = reinterpret_cast<uint32_t*>(sT + 512);  // [2 wg][2 st][4]
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sZ + 16);
+  int32_t* sT = reinterpret_cast<int32_t*>(sP + 65536);  // [2 h][2 st][128]
+  uint32_t* sZ = reinterpret_cast<uint32_t*>(sT + 512);  // [2 h][2 st][4]
+  float* sX = reinterpret_cast<float*>(sZ + 16);          // [2 h][2 half][128] partial row max / row sum
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sX + 512);
   uint64_t* bar_k = bar_q + 1;    // [2]
   uint64_t* bar_v = bar_k + 2;    // [2]
   uint64_t* bar_s = bar_v + 2;    // [2]
@@ -49,15 +57,15 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p)
   const int g = h0 / hpg;
   const long long row_base = (long long)b * p.row_len;
 
-  if (tid == 256) {
+  if (tid == 512) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(bar_q, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_k[i], 1); mbar_init(&bar_v[i], 1); mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 128); mbar_init(&bar_pv[i], 1);
+      mbar_init(&bar_k[i], 1); mbar_init(&bar_v[i], 1); mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 256); mbar_init(&bar_pv[i], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc<512>(tmem_slot);
+  if (warp == 16) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -67,7 +75,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p)
   const int kv_hi = (p.seg_end[row_base + qt * 128 + 127] + 127) >> 7;
   const int n_kv = kv_hi - kv_lo;
 
-  if (warp == 8) {
+  if (warp == 16) {
     if (lane == 0) {
       // ------------------------------------------------ issue thread ----------
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
@@ -99,21 +107,24 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p)
         const int st = j & 1;
         for (int h = 0; h < 2; ++h) {
           mbar_wait(&bar_p[h], j & 1);                    // P_h(j) in smem, S_h(j) and PV_h(j-1) consumed
-          if (h == 0) mbar_wait(&bar_v[st], (j >> 1) & 1);
           tc_fence_after();
-          const uint32_t pa = smem_u32(sP + h * 32768), va = smem_u32(sV + st * 16384);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem + 256 + h * 64, umma_desc_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024),
-                      umma_desc_sw128(va + k * 2048, 16384, 1024), idesc_pv, k > 0);
-          umma_commit(&bar_pv[h]);
-          if (j + 1 < n_kv) {
+          if (j + 1 < n_kv) {  // next S first: the softmax warps need it before they need PV_h(j)
             if (h == 0) {
               mbar_wait(&bar_k[st ^ 1], ((j + 1) >> 1) & 1);
               tc_fence_after();
             }
             issue_s(h, st ^ 1);
           }
+          if (h == 0) {
+            mbar_wait(&bar_v[st], (j >> 1) & 1);
+            tc_fence_after();
+          }
+          const uint32_t pa = smem_u32(sP + h * 32768), va = smem_u32(sV + st * 16384);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem + 256 + h * 64, umma_desc_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024),
+                      umma_desc_sw128(va + k * 2048, 16384, 1024), idesc_pv, k > 0);
+          umma_commit(&bar_pv[h]);
         }
         if (j + 2 < n_kv) {  // refill stage st with tile j+2: its S MMAs retired (bar_p seen), wait for its PV MMAs
           const int kr = (int)(row_base + (long long)(kv_lo + j + 2) * 128);
@@ -127,50 +138,68 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p)
       }
     }
   } else {
-    // -------------------------------------------------- softmax warpgroups ----
-    const int wg = warp >> 2, t = tid & 127, wq = warp & 3;
-    const int h = h0 + wg;
+    // -------------------------------------------------- softmax warps ---------
+    const int hh = warp >> 3, half = (warp >> 2) & 1, wq = warp & 3;
+    const int t = wq * 32 + lane;                       // accumulator row
+    const int h = h0 + hh;
     const long long tq = row_base + qt * 128 + t;
     const int tmq = p.tm[tq];
     const int qs = p.seg_start[tq], qe = p.seg_end[tq];
-    const uint32_t t_s = tmem + ((uint32_t)(wq * 32) << 16) + wg * 128;
-    const uint32_t t_pv = tmem + ((uint32_t)(wq * 32) << 16) + 256 + wg * 64;
-    uint8_t* sPh = sP + wg * 32768;
-    int32_t* sTw = sT + wg * 256;
-    uint32_t* sZw = sZ + wg * 8;
-    float o[64];
+    const uint32_t t_s = tmem + ((uint32_t)(wq * 32) << 16) + hh * 128 + half * 64;
+    const uint32_t t_pv = tmem + ((uint32_t)(wq * 32) << 16) + 256 + hh * 64 + half * 32;
+    uint8_t* sPblk = sP + hh * 32768 + half * 16384;     // this half's 64-column K-block of P_h
+    int32_t* sTh = sT + hh * 256;
+    uint32_t* sZh = sZ + hh * 8;
+    float* sXmine = sX + (hh * 2 + half) * 128;
+    float* sXother = sX + (hh * 2 + (half ^ 1)) * 128;
+    float o[32];
 #pragma unroll
-    for (int c = 0; c < 64; ++c) o[c] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    for (int c = 0; c < 32; ++c) o[c] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+
+    // mask ids of a tile's keys are staged one tile ahead; the per-tile head barrier (row max
+    // exchange) also publishes them
+    int tk_next = 0;
+    auto load_ids = [&](int jj) {  // issue the global load early ...
+      if (half == 0 && jj < n_kv) tk_next = p.tm[row_base + (long long)(kv_lo + jj) * 128 + t];
+    };
+    auto publish_ids = [&](int jj) {  // ... and consume it a phase later
+      if (half == 0 && jj < n_kv) {
+        sTh[(jj & 1) * 128 + t] = tk_next;
+        const uint32_t z = __ballot_sync(0xffffffffu, tk_next == 0);
+        if (lane == 0) sZh[(jj & 1) * 4 + wq] = z;
+      }
+    };
+    load_ids(0);
+    publish_ids(0);
+    head_sync(hh);
 
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
       const int tile0 = (kv_lo + j) * 128;
-      {
-        const int tk = p.tm[row_base + tile0 + t];
-        sTw[st * 128 + t] = tk;
-        const uint32_t z = __ballot_sync(0xffffffffu, tk == 0);
-        if (lane == 0) sZw[st * 4 + wq] = z;
-      }
-      wg_sync(wg);
-      uint32_t vw[4];
+      load_ids(j + 1);
+      uint32_t vw[2], rw[2];
       {
         const int lo = qs - tile0, hi = qe - tile0;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const uint32_t r = range_word(lo, hi, w), z = sZw[st * 4 + w];
-          vw[w] = (r & z) | ((tmq != 0) ? equal_id_word(r, z, sTw + st * 128 + w * 32, tmq) : 0u);
+        for (int w = 0; w < 2; ++w) {
+          const int ww = half * 2 + w;
+          const uint32_t r = range_word(lo, hi, ww), z = sZh[st * 4 + ww];
+          rw[w] = r;
+          vw[w] = (r & z) | ((tmq != 0) ? equal_id_word(r, z, sTh + st * 128 + ww * 32, tmq) : 0u);
         }
       }
-      mbar_wait(&bar_s[wg], j & 1);
+      mbar_wait(&bar_s[hh], j & 1);
       tc_fence_after();
-      float mx = m_run;
+      // row max over the run's columns (a superset of the visible ones: any upper bound of the
+      // visible scores stabilises the softmax identically, and only run edges need a select)
+      float mx = -INFINITY;
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const uint32_t w = vw[c4];
-        if (!__any_sync(0xffffffffu, w != 0u)) continue;
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const uint32_t w = rw[c2];
+        if (!__any_sync(0xffffffffu, vw[c2] != 0u)) continue;
         float s[32];
-        tmem_ld_32x32_f(t_s + c4 * 32, s);
+        tmem_ld_32x32_f(t_s + c2 * 32, s);
         if (__all_sync(0xffffffffu, w == 0xffffffffu)) {
 #pragma unroll
           for (int c = 0; c < 32; ++c) mx = fmaxf(mx, s[c]);
@@ -179,79 +208,92 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p)
           for (int c = 0; c < 32; ++c) mx = fmaxf(mx, (w >> c) & 1u ? s[c] : -INFINITY);
         }
       }
+      sXmine[t] = mx;
+      publish_ids(j + 1);
+      head_sync(hh);
+      mx = fmaxf(fmaxf(mx, sXother[t]), m_run);
+      // deferred O update of the previous tile: its PV MMA was issued before this tile's S
+      if (j > 0) {
+        mbar_wait(&bar_pv[hh], (j - 1) & 1);
+        tc_fence_after();
+        float v[32];
+        tmem_ld_32x32_f(t_pv, v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) o[c] = fmaf(o[c], alpha_prev, v[c]);
+      }
       const float alpha = (m_run == -INFINITY) ? 0.f : ex2((m_run - mx) * kScaleLog2);
       const float mscaled = (mx == -INFINITY) ? 0.f : mx * kScaleLog2;
       float lsum = 0.f;
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const uint32_t w = vw[c4];
-        uint8_t* blk = sPh + (c4 >> 1) * 16384;
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const uint32_t w = vw[c2];
         uint32_t pk[16];
         if (!__any_sync(0xffffffffu, w != 0u)) {
 #pragma unroll
           for (int q = 0; q < 16; ++q) pk[q] = 0u;
         } else {
           float s[32];
-          tmem_ld_32x32_f(t_s + c4 * 32, s);
-          if (__all_sync(0xffffffffu, w == 0xffffffffu)) {
+          tmem_ld_32x32_f(t_s + c2 * 32, s);
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              const float p0 = ex2(fmaf(s[c], kScaleLog2, -mscaled)), p1 = ex2(fmaf(s[c + 1], kScaleLog2, -mscaled));
-              lsum += p0 + p1;
-              pk[c >> 1] = pack_bf16(p0, p1);
-            }
-          } else {
+          for (int g8 = 0; g8 < 4; ++g8) {  // 8 columns at a time: masked keys are sparse, most groups are clean
+            const uint32_t wb = (w >> (8 * g8)) & 0xffu;
+            if (__all_sync(0xffffffffu, wb == 0xffu)) {
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              const float p0 = (w >> c) & 1u ? ex2(fmaf(s[c], kScaleLog2, -mscaled)) : 0.f;
-              const float p1 = (w >> (c + 1)) & 1u ? ex2(fmaf(s[c + 1], kScaleLog2, -mscaled)) : 0.f;
-              lsum += p0 + p1;
-              pk[c >> 1] = pack_bf16(p0, p1);
+              for (int c = 8 * g8; c < 8 * g8 + 8; c += 2) {
+                const float p0 = ex2(fmaf(s[c], kScaleLog2, -mscaled)), p1 = ex2(fmaf(s[c + 1], kScaleLog2, -mscaled));
+                lsum += p0 + p1;
+                pk[c >> 1] = pack_bf16(p0, p1);
+              }
+            } else {
+#pragma unroll
+              for (int c = 8 * g8; c < 8 * g8 + 8; c += 2) {
+                const float p0 = (w >> c) & 1u ? ex2(fmaf(s[c], kScaleLog2, -mscaled)) : 0.f;
+                const float p1 = (w >> (c + 1)) & 1u ? ex2(fmaf(s[c + 1], kScaleLog2, -mscaled)) : 0.f;
+                lsum += p0 + p1;
+                pk[c >> 1] = pack_bf16(p0, p1);
+              }
             }
           }
         }
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
-          *reinterpret_cast<uint4*>(blk + sw128_off(t, (c4 & 1) * 4 + q4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+          *reinterpret_cast<uint4*>(sPblk + sw128_off(t, c2 * 4 + q4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
       }
       l_run = l_run * alpha + lsum;
       m_run = mx;
+      alpha_prev = alpha;
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(&bar_p[wg]);
-      mbar_wait(&bar_pv[wg], j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {
-        float v[32];
-        tmem_ld_32x32_f(t_pv + c2 * 32, v);
-#pragma unroll
-        for (int c = 0; c < 32; ++c) o[c2 * 32 + c] = fmaf(o[c2 * 32 + c], alpha, v[c]);
-      }
+      mbar_arrive(&bar_p[hh]);
     }
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    __nv_bfloat16* orow = p.out + tq * (long long)(p.H * 64) + h * 64;
+    // last tile's O update, then normalise with the row sum of both halves
+    mbar_wait(&bar_pv[hh], (n_kv - 1) & 1);
+    tc_fence_after();
+    {
+      float v[32];
+      tmem_ld_32x32_f(t_pv, v);
 #pragma unroll
-    for (int q8 = 0; q8 < 8; ++q8) {
-      uint4 u;
-      u.x = pack_bf16(o[8 * q8] * inv, o[8 * q8 + 1] * inv);
-      u.y = pack_bf16(o[8 * q8 + 2] * inv, o[8 * q8 + 3] * inv);
-      u.z = pack_bf16(o[8 * q8 + 4] * inv, o[8 * q8 + 5] * inv);
-      u.w = pack_bf16(o[8 * q8 + 6] * inv, o[8 * q8 + 7] * inv);
-      reinterpret_cast<uint4*>(orow)[q8] = u;
+      for (int c = 0; c < 32; ++c) o[c] = fmaf(o[c], alpha_prev, v[c]);
     }
-    p.lse2[(long long)h * p.T + tq] = (l_run > 0.f) ? (m_run * kScaleLog2 + log2f(l_run)) : 0.f;
+    head_sync(hh);            // everyone is past its last read of the max-exchange slots
+    sXmine[t] = l_run;
+    head_sync(hh);
+    const float l_tot = l_run + sXother[t];
+    const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+    __nv_bfloat16* orow = p.out + tq * (long long)(p.H * 64) + h * 64 + half * 32;
+    store_row_bf16_32(orow, o, inv);
+    if (half == 0) p.lse2[(long long)h * p.T + tq] = (l_tot > 0.f) ? (m_run * kScaleLog2 + log2f(l_tot)) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 16) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
 }
 
 // ================================================================ dQ ==========
-// CTA = (128-query tile, head pair); 64-key tiles.
+// CTA = (128-query tile, head pair); 64-key tiles; a thread owns a row and 32 of the 64 columns.
 // smem per head: Q 16K | dO 16K | dS 16K ; shared: K 2x8K | V 2x8K ; ids ; barriers
 constexpr int DQP_SMEM = 2 * 49152 + 4 * 8192 + 2 * 2 * 64 * 4 + 2 * 2 * 2 * 4 + 256 + 1024;
 
@@ -259,14 +301,14 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1)
 attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                     const __grid_constant__ CUtensorMap tmDO128, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = smem_align1024(smem_raw);
   uint8_t* sQ = base;                  // [2][16K]
   uint8_t* sDO = sQ + 32768;           // [2][16K]
   uint8_t* sDS = sDO + 32768;          // [2][16K]
   uint8_t* sK = sDS + 32768;           // [2 st][8K]
   uint8_t* sV = sK + 16384;            // [2 st][8K]
-  int32_t* sT = reinterpret_cast<int32_t*>(sV + 16384);  // [2 wg][2 st][64]
-  uint32_t* sZ = reinterpret_cast<uint32_t*>(sT + 256);  // [2 wg][2 st][2]
+  int32_t* sT = reinterpret_cast<int32_t*>(sV + 16384);  // [2 h][2 st][64]
+  uint32_t* sZ = reinterpret_cast<uint32_t*>(sT + 256);  // [2 h][2 st][2]
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(sZ + 8);
   uint64_t* bar_kv = bar_q + 1;   // [2]
   uint64_t* bar_s = bar_kv + 2;   // [2]
@@ -285,14 +327,14 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
   const int g = h0 / hpg;
   const long long row_base = (long long)b * p.row_len;
 
-  if (tid == 256) {
+  if (tid == 512) {
     mbar_init(bar_q, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_kv[i], 1); mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 128); mbar_init(&bar_dq[i], 1);
+      mbar_init(&bar_kv[i], 1); mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 256); mbar_init(&bar_dq[i], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc<512>(tmem_slot);
+  if (warp == 16) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -302,7 +344,7 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
   const int kv_hi = (p.seg_end[row_base + qt * 128 + 127] + 63) >> 6;
   const int n_kv = kv_hi - kv_lo;
 
-  if (warp == 8) {
+  if (warp == 16) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);
@@ -339,19 +381,19 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
         for (int h = 0; h < 2; ++h) {
           mbar_wait(&bar_p[h], j & 1);  // dS_h(j) in smem; S_h/dP_h(j) consumed
           tc_fence_after();
-          const uint32_t sa = smem_u32(sDS + h * 16384), ka = smem_u32(sK + st * 8192);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + h * 192 + 128, umma_desc_sw128(sa + k * 32, 0, 1024), umma_desc_sw128(ka + k * 2048, 8192, 1024), idesc_dq,
-                      (j > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&bar_dq[h]);
-          if (j + 1 < n_kv) {
+          if (j + 1 < n_kv) {  // next S/dP first: the elementwise warps wait on them, not on dQ
             if (h == 0) {
               mbar_wait(&bar_kv[st ^ 1], ((j + 1) >> 1) & 1);
               tc_fence_after();
             }
             issue_s(h, st ^ 1);
           }
+          const uint32_t sa = smem_u32(sDS + h * 16384), ka = smem_u32(sK + st * 8192);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + h * 192 + 128, umma_desc_sw128(sa + k * 32, 0, 1024), umma_desc_sw128(ka + k * 2048, 8192, 1024), idesc_dq,
+                      (j > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&bar_dq[h]);
         }
         if (j + 2 < n_kv) {  // stage st is free once both dQ MMAs of tile j retired
           mbar_wait(&bar_dq[0], j & 1);
@@ -364,107 +406,106 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
       }
     }
   } else {
-    const int wg = warp >> 2, t = tid & 127, wq = warp & 3;
-    const int h = h0 + wg;
+    const int hh = warp >> 3, half = (warp >> 2) & 1, wq = warp & 3;
+    const int t = wq * 32 + lane;
+    const int h = h0 + hh;
     const long long tq = row_base + qt * 128 + t;
     const int tmq = p.tm[tq];
     const int qs = p.seg_start[tq], qe = p.seg_end[tq];
     const float lse2 = p.lse2[(long long)h * p.T + tq];
     const float dlt_s = p.delta[(long long)h * p.T + tq] * kScale;
-    const uint32_t t_b = tmem + ((uint32_t)(wq * 32) << 16) + wg * 192;
-    uint8_t* sDSh = sDS + wg * 16384;
-    int32_t* sTw = sT + wg * 128;
-    uint32_t* sZw = sZ + wg * 4;
+    const uint32_t t_b = tmem + ((uint32_t)(wq * 32) << 16) + hh * 192;
+    uint8_t* sDSh = sDS + hh * 16384;
+    int32_t* sTh = sT + hh * 128;
+    uint32_t* sZh = sZ + hh * 4;
 
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
       const int tile0 = (kv_lo + j) * 64;
-      if (t < 64) {
+      if (half == 0 && t < 64) {
         const int tk = p.tm[row_base + tile0 + t];
-        sTw[st * 64 + t] = tk;
+        sTh[st * 64 + t] = tk;
         const uint32_t z = __ballot_sync(0xffffffffu, tk == 0);
-        if (lane == 0) sZw[st * 2 + wq] = z;
+        if (lane == 0) sZh[st * 2 + wq] = z;
       }
-      wg_sync(wg);
-      uint32_t vw[2];
+      head_sync(hh);
+      uint32_t w;
       {
-        const int lo = qs - tile0, hi = qe - tile0;
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          const uint32_t r = range_word(lo, hi, w), z = sZw[st * 2 + w];
-          vw[w] = (r & z) | ((tmq != 0) ? equal_id_word(r, z, sTw + st * 64 + w * 32, tmq) : 0u);
-        }
+        const uint32_t r = range_word(qs - tile0, qe - tile0, half), z = sZh[st * 2 + half];
+        w = (r & z) | ((tmq != 0) ? equal_id_word(r, z, sTh + st * 64 + half * 32, tmq) : 0u);
       }
-      mbar_wait(&bar_s[wg], j & 1);
-      if (j > 0) mbar_wait(&bar_dq[wg], (j - 1) & 1);  // dS buffer free
+      mbar_wait(&bar_s[hh], j & 1);
+      if (j > 0) mbar_wait(&bar_dq[hh], (j - 1) & 1);  // dS buffer free
       tc_fence_after();
+      uint32_t pk[16];
+      if (!__any_sync(0xffffffffu, w != 0u)) {
 #pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {
-        const uint32_t w = vw[c2];
-        uint32_t pk[16];
-        if (!__any_sync(0xffffffffu, w != 0u)) {
+        for (int q = 0; q < 16; ++q) pk[q] = 0u;
+      } else {
+        float s[32], dp[32];
+        tmem_ld_32x32_f(t_b + half * 32, s);
+        tmem_ld_32x32_f(t_b + 64 + half * 32, dp);
 #pragma unroll
-          for (int q = 0; q < 16; ++q) pk[q] = 0u;
-        } else {
-          float s[32], dp[32];
-          tmem_ld_32x32_f(t_b + c2 * 32, s);
-          tmem_ld_32x32_f(t_b + 64 + c2 * 32, dp);
-          const bool full = __all_sync(0xffffffffu, w == 0xffffffffu);
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const uint32_t wb = (w >> (8 * g8)) & 0xffu;
+          if (__all_sync(0xffffffffu, wb == 0xffu)) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            float p0 = ex2(fmaf(s[c], kScaleLog2, -lse2)), p1 = ex2(fmaf(s[c + 1], kScaleLog2, -lse2));
-            if (!full) {
-              p0 = (w >> c) & 1u ? p0 : 0.f;
-              p1 = (w >> (c + 1)) & 1u ? p1 : 0.f;
+            for (int c = 8 * g8; c < 8 * g8 + 8; c += 2) {
+              const float p0 = ex2(fmaf(s[c], kScaleLog2, -lse2)), p1 = ex2(fmaf(s[c + 1], kScaleLog2, -lse2));
+              pk[c >> 1] = pack_bf16(p0 * fmaf(dp[c], kScale, -dlt_s), p1 * fmaf(dp[c + 1], kScale, -dlt_s));
             }
-            pk[c >> 1] = pack_bf16(p0 * fmaf(dp[c], kScale, -dlt_s), p1 * fmaf(dp[c + 1], kScale, -dlt_s));
+          } else {
+#pragma unroll
+            for (int c = 8 * g8; c < 8 * g8 + 8; c += 2) {
+              const float p0 = (w >> c) & 1u ? ex2(fmaf(s[c], kScaleLog2, -lse2)) : 0.f;
+              const float p1 = (w >> (c + 1)) & 1u ? ex2(fmaf(s[c + 1], kScaleLog2, -lse2)) : 0.f;
+              pk[c >> 1] = pack_bf16(p0 * fmaf(dp[c], kScale, -dlt_s), p1 * fmaf(dp[c + 1], kScale, -dlt_s));
+            }
           }
         }
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          *reinterpret_cast<uint4*>(sDSh + sw128_off(t, c2 * 4 + q4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
       }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4)
+        *reinterpret_cast<uint4*>(sDSh + sw128_off(t, half * 4 + q4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(&bar_p[wg]);
+      mbar_arrive(&bar_p[hh]);
     }
-    mbar_wait(&bar_dq[wg], (n_kv - 1) & 1);
+    mbar_wait(&bar_dq[hh], (n_kv - 1) & 1);
     tc_fence_after();
-    __nv_bfloat16* drow = p.dqkv + tq * p.ld + h * 64;
-#pragma unroll
-    for (int c2 = 0; c2 < 2; ++c2) {
-      float v[32];
-      tmem_ld_32x32_f(t_b + 128 + c2 * 32, v);
-      store_row_bf16_32(drow + c2 * 32, v, 1.f);
-    }
+    __nv_bfloat16* drow = p.dqkv + tq * p.ld + h * 64 + half * 32;
+    float v[32];
+    tmem_ld_32x32_f(t_b + 128 + half * 32, v);
+    store_row_bf16_32(drow, v, 1.f);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 16) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
 }
 
 // ================================================================ dK/dV =======
-// CTA = (128-key tile, kv head); warpgroup w walks heads g*hpg + w + 2i and their 64-query tiles.
-// smem: K 16K | V 16K | per wg: Q 2x8K, dO 2x8K, Pt 16K, dSt 16K | per-query scalars | barriers
+// CTA = (128-key tile, kv head); head slot w walks heads g*hpg + w + 2i and their 64-query tiles;
+// a thread owns a key row and 32 of the tile's 64 query columns.
+// smem: K 16K | V 16K | per slot: Q 2x8K, dO 2x8K, Pt 16K, dSt 16K | per-query scalars | barriers
 constexpr int DKVP_SMEM = 32768 + 2 * 65536 + 2 * 2 * 3 * 64 * 4 + 2 * 2 * 2 * 4 + 256 + 1024;
 
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                      const __grid_constant__ CUtensorMap tmDO64, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = smem_align1024(smem_raw);
   uint8_t* sK = base;
   uint8_t* sV = sK + 16384;
-  uint8_t* sW = sV + 16384;  // per wg 64K: Q [2][8K] | dO [2][8K] | Pt 16K | dSt 16K
-  int32_t* sT = reinterpret_cast<int32_t*>(sW + 131072);  // [2 wg][2 st][64]
-  float* sL = reinterpret_cast<float*>(sT + 256);         // [2 wg][2 st][64] lse2
-  float* sD = sL + 256;                                    // [2 wg][2 st][64] delta*scale
-  uint32_t* sZ = reinterpret_cast<uint32_t*>(sD + 256);   // [2 wg][2 st][2]
+  uint8_t* sW = sV + 16384;  // per slot 64K: Q [2][8K] | dO [2][8K] | Pt 16K | dSt 16K
+  int32_t* sT = reinterpret_cast<int32_t*>(sW + 131072);  // [2 slot][2 st][64]
+  float* sL = reinterpret_cast<float*>(sT + 256);         // [2 slot][2 st][64] lse2
+  float* sD = sL + 256;                                    // [2 slot][2 st][64] delta*scale
+  uint32_t* sZ = reinterpret_cast<uint32_t*>(sD + 256);   // [2 slot][2 st][2]
   uint64_t* bar_k = reinterpret_cast<uint64_t*>(sZ + 8);
-  uint64_t* bar_q = bar_k + 1;     // [2 wg][2 st]
+  uint64_t* bar_q = bar_k + 1;     // [2 slot][2 st]
   uint64_t* bar_s = bar_q + 4;     // [2]
   uint64_t* bar_p = bar_s + 2;     // [2]
   uint64_t* bar_acc = bar_p + 2;   // [2]
@@ -479,13 +520,13 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
   const int b = bx / p.G;
   const long long row_base = (long long)b * p.row_len;
 
-  if (tid == 256) {
+  if (tid == 512) {
     mbar_init(bar_k, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&bar_q[i], 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 128); mbar_init(&bar_acc[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 256); mbar_init(&bar_acc[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc<512>(tmem_slot);
+  if (warp == 16) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -496,7 +537,7 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
   const int n_q = q_hi - q_lo;
   const int n_it = n_q * (hpg >> 1);
 
-  if (warp == 8) {
+  if (warp == 16) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 64, 0, 1);
@@ -536,6 +577,11 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
         for (int w = 0; w < 2; ++w) {
           mbar_wait(&bar_p[w], it & 1);  // Pt_w/dSt_w(it) in smem; St_w/dPt_w(it) consumed
           tc_fence_after();
+          if (it + 1 < n_it) {  // next St/dPt first: the elementwise warps wait on them
+            mbar_wait(&bar_q[w * 2 + (st ^ 1)], ((it + 1) >> 1) & 1);
+            tc_fence_after();
+            issue_s(w, st ^ 1);
+          }
           uint8_t* wb = sW + w * 65536;
           const uint32_t pa = smem_u32(wb + 32768), sa = smem_u32(wb + 49152);
           const uint32_t qa = smem_u32(wb + st * 8192), da = smem_u32(wb + 16384 + st * 8192);
@@ -549,11 +595,6 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
             umma_bf16(tmem + 320, umma_desc_sw128(sa + k * 32, 0, 1024), umma_desc_sw128(qa + k * 2048, 8192, 1024), idesc_acc,
                       (k > 0) ? 1u : first);
           umma_commit(&bar_acc[w]);
-          if (it + 1 < n_it) {
-            mbar_wait(&bar_q[w * 2 + (st ^ 1)], ((it + 1) >> 1) & 1);
-            tc_fence_after();
-            issue_s(w, st ^ 1);
-          }
         }
         if (it + 2 < n_it) {
           for (int w = 0; w < 2; ++w) {
@@ -564,100 +605,98 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
       }
     }
   } else {
-    const int wg = warp >> 2, t = tid & 127, wq = warp & 3;
+    const int hh = warp >> 3, half = (warp >> 2) & 1, wq = warp & 3;
+    const int t = wq * 32 + lane;
     const long long tk = row_base + kt * 128 + t;
     const int tmk = p.tm[tk];
     const int ks = p.seg_start[tk], ke = p.seg_end[tk];
-    const uint32_t t_b = tmem + ((uint32_t)(wq * 32) << 16) + wg * 128;
-    uint8_t* wb = sW + wg * 65536;
+    const uint32_t t_b = tmem + ((uint32_t)(wq * 32) << 16) + hh * 128;
+    uint8_t* wb = sW + hh * 65536;
     uint8_t* sPT = wb + 32768;
     uint8_t* sDST = wb + 49152;
-    int32_t* sTw = sT + wg * 128;
-    float* sLw = sL + wg * 128;
-    float* sDw = sD + wg * 128;
-    uint32_t* sZw = sZ + wg * 4;
+    int32_t* sTh = sT + hh * 128;
+    float* sLh = sL + hh * 128;
+    float* sDh = sD + hh * 128;
+    uint32_t* sZh = sZ + hh * 4;
 
     for (int it = 0; it < n_it; ++it) {
       const int st = it & 1;
-      const int h = g * hpg + wg + 2 * (it / n_q);
+      const int h = g * hpg + hh + 2 * (it / n_q);
       const int tile0 = (q_lo + it % n_q) * 64;
-      if (t < 64) {
+      if (half == 0 && t < 64) {
         const long long q = row_base + tile0 + t;
         const int tqm = p.tm[q];
-        sTw[st * 64 + t] = tqm;
-        sLw[st * 64 + t] = p.lse2[(long long)h * p.T + q];
-        sDw[st * 64 + t] = p.delta[(long long)h * p.T + q] * kScale;
+        sTh[st * 64 + t] = tqm;
+        sLh[st * 64 + t] = p.lse2[(long long)h * p.T + q];
+        sDh[st * 64 + t] = p.delta[(long long)h * p.T + q] * kScale;
         const uint32_t z = __ballot_sync(0xffffffffu, tqm == 0);
-        if (lane == 0) sZw[st * 2 + wq] = z;
+        if (lane == 0) sZh[st * 2 + wq] = z;
       }
-      wg_sync(wg);
-      uint32_t vw[2];
+      head_sync(hh);
+      uint32_t w;
       {
-        const int lo = ks - tile0, hi = ke - tile0;
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          const uint32_t r = range_word(lo, hi, w);
-          vw[w] = (tmk == 0) ? r : equal_id_word(r, sZw[st * 2 + w], sTw + st * 64 + w * 32, tmk);
-        }
+        const uint32_t r = range_word(ks - tile0, ke - tile0, half);
+        w = (tmk == 0) ? r : equal_id_word(r, sZh[st * 2 + half], sTh + st * 64 + half * 32, tmk);
       }
-      mbar_wait(&bar_s[wg], it & 1);
-      if (it > 0) mbar_wait(&bar_acc[wg], (it - 1) & 1);  // Pt/dSt buffers free
+      mbar_wait(&bar_s[hh], it & 1);
+      if (it > 0) mbar_wait(&bar_acc[hh], (it - 1) & 1);  // Pt/dSt buffers free
       tc_fence_after();
-      const float* sl = sLw + st * 64;
-      const float* sd = sDw + st * 64;
+      const float* sl = sLh + st * 64 + half * 32;
+      const float* sd = sDh + st * 64 + half * 32;
+      uint32_t pp[16], pd[16];
+      if (!__any_sync(0xffffffffu, w != 0u)) {
 #pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {
-        const uint32_t w = vw[c2];
-        uint32_t pp[16], pd[16];
-        if (!__any_sync(0xffffffffu, w != 0u)) {
+        for (int q = 0; q < 16; ++q) { pp[q] = 0u; pd[q] = 0u; }
+      } else {
+        float s[32], dp[32];
+        tmem_ld_32x32_f(t_b + half * 32, s);
+        tmem_ld_32x32_f(t_b + 64 + half * 32, dp);
 #pragma unroll
-          for (int q = 0; q < 16; ++q) { pp[q] = 0u; pd[q] = 0u; }
-        } else {
-          float s[32], dp[32];
-          tmem_ld_32x32_f(t_b + c2 * 32, s);
-          tmem_ld_32x32_f(t_b + 64 + c2 * 32, dp);
-          const bool full = __all_sync(0xffffffffu, w == 0xffffffffu);
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const uint32_t wb = (w >> (8 * g8)) & 0xffu;
+          const bool clean = __all_sync(0xffffffffu, wb == 0xffu);
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const int qc = c2 * 32 + c;
-            const float2 l2 = *reinterpret_cast<const float2*>(sl + qc);
-            const float2 d2 = *reinterpret_cast<const float2*>(sd + qc);
-            float p0 = ex2(fmaf(s[c], kScaleLog2, -l2.x)), p1 = ex2(fmaf(s[c + 1], kScaleLog2, -l2.y));
-            if (!full) {
+          for (int c = 8 * g8; c < 8 * g8 + 8; c += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(sl + c);
+            const float4 d4 = *reinterpret_cast<const float4*>(sd + c);
+            float p0 = ex2(fmaf(s[c], kScaleLog2, -l4.x)), p1 = ex2(fmaf(s[c + 1], kScaleLog2, -l4.y));
+            float p2 = ex2(fmaf(s[c + 2], kScaleLog2, -l4.z)), p3 = ex2(fmaf(s[c + 3], kScaleLog2, -l4.w));
+            if (!clean) {
               p0 = (w >> c) & 1u ? p0 : 0.f;
               p1 = (w >> (c + 1)) & 1u ? p1 : 0.f;
+              p2 = (w >> (c + 2)) & 1u ? p2 : 0.f;
+              p3 = (w >> (c + 3)) & 1u ? p3 : 0.f;
             }
             pp[c >> 1] = pack_bf16(p0, p1);
-            pd[c >> 1] = pack_bf16(p0 * fmaf(dp[c], kScale, -d2.x), p1 * fmaf(dp[c + 1], kScale, -d2.y));
+            pp[(c >> 1) + 1] = pack_bf16(p2, p3);
+            pd[c >> 1] = pack_bf16(p0 * fmaf(dp[c], kScale, -d4.x), p1 * fmaf(dp[c + 1], kScale, -d4.y));
+            pd[(c >> 1) + 1] = pack_bf16(p2 * fmaf(dp[c + 2], kScale, -d4.z), p3 * fmaf(dp[c + 3], kScale, -d4.w));
           }
         }
+      }
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const uint32_t off = sw128_off(t, c2 * 4 + q4);
-          *reinterpret_cast<uint4*>(sPT + off) = make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
-          *reinterpret_cast<uint4*>(sDST + off) = make_uint4(pd[4 * q4], pd[4 * q4 + 1], pd[4 * q4 + 2], pd[4 * q4 + 3]);
-        }
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint32_t off = sw128_off(t, half * 4 + q4);
+        *reinterpret_cast<uint4*>(sPT + off) = make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
+        *reinterpret_cast<uint4*>(sDST + off) = make_uint4(pd[4 * q4], pd[4 * q4 + 1], pd[4 * q4 + 2], pd[4 * q4 + 3]);
       }
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(&bar_p[wg]);
+      mbar_arrive(&bar_p[hh]);
     }
-    // both warpgroups' accumulate MMAs must have retired; wg 0 stores dV, wg 1 stores dK
+    // both slots' accumulate MMAs must have retired; slot 0 stores dV, slot 1 stores dK
     mbar_wait(&bar_acc[0], (n_it - 1) & 1);
     mbar_wait(&bar_acc[1], (n_it - 1) & 1);
     tc_fence_after();
-    const uint32_t t_acc = tmem + ((uint32_t)(wq * 32) << 16) + 256 + wg * 64;
-    __nv_bfloat16* drow = p.dqkv + tk * p.ld + (wg == 0 ? p.v_col : p.k_col) + g * 64;
-#pragma unroll
-    for (int c2 = 0; c2 < 2; ++c2) {
-      float v[32];
-      tmem_ld_32x32_f(t_acc + c2 * 32, v);
-      store_row_bf16_32(drow + c2 * 32, v, 1.f);
-    }
+    const uint32_t t_acc = tmem + ((uint32_t)(wq * 32) << 16) + 256 + hh * 64 + half * 32;
+    __nv_bfloat16* drow = p.dqkv + tk * p.ld + (hh == 0 ? p.v_col : p.k_col) + g * 64 + half * 32;
+    float v[32];
+    tmem_ld_32x32_f(t_acc, v);
+    store_row_bf16_32(drow, v, 1.f);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 16) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }

@@ -28,7 +28,7 @@ constexpr int FWD_SMEM = 16384 + 2 * 16384 + 16384 + 32768 + 2 * 128 * 4 + 2 * 4
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = smem_align1024(smem_raw);
   uint8_t* sQ = base;
   uint8_t* sK = sQ + 16384;
   uint8_t* sV = sK + 2 * 16384;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(128, 2)
 attn_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                const __grid_constant__ CUtensorMap tmDO128, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = smem_align1024(smem_raw);
   uint8_t* sQ = base;
   uint8_t* sDO = sQ + 16384;
   uint8_t* sK = sDO + 16384;   // [2][8K]
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(128, 2)
 attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                 const __grid_constant__ CUtensorMap tmDO64, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = smem_align1024(smem_raw);
   uint8_t* sK = base;
   uint8_t* sV = sK + 16384;
   uint8_t* sQ = sV + 16384;     // [2][8K]

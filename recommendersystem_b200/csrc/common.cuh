@@ -41,6 +41,10 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+// 1024-byte alignment (128B swizzle atoms) by pointer arithmetic on the __shared__ array, so
+// the compiler keeps the shared address space (a uintptr_t round trip degrades every access
+// to generic LD/ST)
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* p) { return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u); }
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

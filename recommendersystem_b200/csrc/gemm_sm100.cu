@@ -165,7 +165,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = smem_align1024(smem_raw);
   uint8_t* sA = base;
   uint8_t* sB = base + STAGES * Cfg::A_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
