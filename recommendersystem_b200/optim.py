@@ -47,9 +47,18 @@ class FlatAdamW:
         self.flat_g.zero_()
 
     def all_reduce_grads(self):
-        """Data-parallel mean of the dense gradient: one collective on the flat buffer."""
+        """Data-parallel reduction of the dense gradient: ONE collective on the flat buffer
+        (the reference's DDP reducer, transformer.py:272/678-682, moves the same bytes in 25 MB
+        buckets).  The sum is reduced; the 1/world of DDP's mean is folded into the clip scale
+        that AdamW applies anyway, so no extra pass over the buffer is made."""
         if self.world > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.AVG)
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+
+    def clip_scale(self, sumsq):
+        """Scale applied to the (summed) gradient: DDP mean x clip_grad_norm_(max_norm)
+        (transformer.py:273): min(1, max_norm / (||g_mean|| + 1e-6)) / world, on device."""
+        norm_mean = sumsq.sqrt() / self.world
+        return torch.clamp(self.max_norm / (norm_mean + 1e-6), max=1.0) / self.world
 
     def step(self, lr=None):
         self.steps += 1
@@ -58,7 +67,7 @@ class FlatAdamW:
         # clip_grad_norm_(params, max_norm): scale = min(1, max_norm / (norm + 1e-6)), on device
         self._sq.zero_()
         L.sumsq(self.flat_g, self._sq)
-        torch.clamp(self.max_norm / (self._sq.sqrt() + 1e-6), max=1.0, out=self._scale)
+        self._scale.copy_(self.clip_scale(self._sq))
         b1, b2 = self.betas
         nd = self.n_decay
         L.adamw(self.flat_p[:nd], self.flat_g[:nd], self.m[:nd], self.v[:nd], lr, b1, b2, self.eps, self.wd, self.steps, self._scale)
@@ -66,4 +75,5 @@ class FlatAdamW:
             L.adamw(self.flat_p[nd:], self.flat_g[nd:], self.m[nd:], self.v[nd:], lr, b1, b2, self.eps, 0.0, self.steps, self._scale)
 
     def grad_norm(self):
-        return self._sq.sqrt()
+        """Global L2 norm of the rank-averaged gradient of the last step (device tensor)."""
+        return self._sq.sqrt() / self.world
