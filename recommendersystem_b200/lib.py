@@ -45,6 +45,8 @@ class GemmArgs(C.Structure):
         ("aux", vp), ("ldaux", i64),
         ("ce_pmax", vp), ("ce_psum", vp), ("ce_tgt", vp), ("ce_target", vp), ("ce_lse", vp), ("ce_coef", vp),
         ("n_offset", i32), ("split_k", C.c_int),
+        ("m_count", vp), ("k_count", vp),
+        ("rope_cos", vp), ("rope_sin", vp), ("rope_pos", vp), ("rope_cols", C.c_int), ("rope_row_len", C.c_int),
     ]
 
 
@@ -56,7 +58,8 @@ class AttnArgs(C.Structure):
     ]
 
 
-EPI_BF16, EPI_F32, EPI_F32_ACCUM, EPI_RESID, EPI_BIAS_BF16, EPI_BIAS_GELU, EPI_CE_PARTIAL, EPI_CE_GRAD, EPI_TABLE = range(9)
+(EPI_BF16, EPI_F32, EPI_F32_ACCUM, EPI_RESID, EPI_BIAS_BF16, EPI_BIAS_GELU, EPI_CE_PARTIAL, EPI_CE_GRAD, EPI_TABLE,
+ EPI_SWIGLU, EPI_ROPE) = range(11)
 
 _lib = None
 
@@ -204,7 +207,7 @@ def scatter_add_sorted(g, g_stride, idx, d, grad_table):
 
 # --------------------------------------------------------------------- GEMM --
 def gemm(A, B, Cout, M, N, K, *, a_kmajor=True, b_kmajor=True, lda=None, ldb=None, ldc=None, epilogue=EPI_BF16,
-         resid=None, ldr=None, bias=None, aux=None, ldaux=None, ce=None, n_offset=0, split_k=0):
+         resid=None, ldr=None, bias=None, aux=None, ldaux=None, ce=None, n_offset=0, split_k=0, m_count=None, k_count=None, rope=None):
     """C[M,N] = op(A) op(B); see include/graft.h graft_gemm_args.  A/B/C may be
     views: pass explicit leading dimensions."""
     g = GemmArgs()
@@ -224,6 +227,15 @@ def gemm(A, B, Cout, M, N, K, *, a_kmajor=True, b_kmajor=True, lda=None, ldb=Non
             setattr(g, "ce_" + k, vp(v.data_ptr()))
     g.n_offset = n_offset
     g.split_k = split_k
+    if m_count is not None:
+        g.m_count = vp(m_count.data_ptr())
+    if k_count is not None:
+        g.k_count = vp(k_count.data_ptr())
+    if rope is not None:  # dict(cos=, sin=, cols=, row_len=, pos=None)
+        g.rope_cos, g.rope_sin = vp(rope["cos"].data_ptr()), vp(rope["sin"].data_ptr())
+        g.rope_cols, g.rope_row_len = rope["cols"], rope.get("row_len", 0)
+        if rope.get("pos") is not None:
+            g.rope_pos = vp(rope["pos"].data_ptr())
     lib = load()
     need = lib.graft_gemm_scratch_bytes(C.byref(g))
     ws = scratch(need, A.device, slot=1) if need > 0 else None
@@ -265,9 +277,9 @@ def swiglu_fwd(gu, act):
     _check(load().graft_swiglu_fwd(ptr(gu), ptr(act), i64(T), I, stream()), "graft_swiglu_fwd")
 
 
-def swiglu_bwd(gu, dact, dgu):
+def swiglu_bwd(gu, dact, dgu, interleaved64=False):
     T, I = dact.shape
-    _check(load().graft_swiglu_bwd(ptr(gu), ptr(dact), ptr(dgu), i64(T), I, stream()), "graft_swiglu_bwd")
+    _check(load().graft_swiglu_bwd(ptr(gu), ptr(dact), ptr(dgu), i64(T), I, int(interleaved64), stream()), "graft_swiglu_bwd")
 
 
 def cast_bf16(src, dst):
@@ -343,6 +355,11 @@ def scatter_rows_f32(g, sel, parity, dx):
 def ce_finish(pmax, psum, n_blocks, tgt, lab, w, lse, coef, term, loss):
     _check(load().graft_ce_finish(ptr(pmax), ptr(psum), n_blocks, ptr(tgt), tgt.numel(), ptr(lab), ptr(w), ptr(lse), ptr(coef),
                                   ptr(term), ptr(loss), stream()), "graft_ce_finish")
+
+
+def ce_merge_partials(pmax, psum, n_blocks, m_out, s_out):
+    _check(load().graft_ce_merge_partials(ptr(pmax), ptr(psum), n_blocks, m_out.numel(), ptr(m_out), ptr(s_out), stream()),
+           "graft_ce_merge_partials")
 
 
 def rating_tail(h1, w2, b2, lab, w, mean, pred, loss4):

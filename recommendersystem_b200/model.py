@@ -20,6 +20,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from . import comm
 from . import lib as L
 
 ALL_MEDIUMS = [0, 1]
@@ -185,6 +186,7 @@ class _ClozeStep(torch.autograd.Function):
         dm, H, G, I = cfg["embed_dim"], cfg["num_heads"], cfg["num_kv_heads"], cfg["intermediate_dim"]
         nl = cfg["num_layers"]
         assert dm // H == 64, "libgraft attention is built for head_dim 64 (as the reference configs use)"
+        assert I % 64 == 0, "intermediate_dim must be a multiple of 64 (fused gate/up tile layout)"
         QKV = (H + 2 * G) * 64
         V0 = cfg["vocab_sizes"]["0_matchedid"]
         Vt = V0 + cfg["vocab_sizes"]["1_matchedid"]
@@ -197,7 +199,11 @@ class _ClozeStep(torch.autograd.Function):
             L.cast_bf16(W[f"l{i}.q"], qkv_w[: H * 64]); L.cast_bf16(W[f"l{i}.k"], qkv_w[H * 64:(H + G) * 64])
             L.cast_bf16(W[f"l{i}.v"], qkv_w[(H + G) * 64:])
             o_w = _bf16((dm, H * 64), dev); L.cast_bf16(W[f"l{i}.o"], o_w)
-            w13 = _bf16((2 * I, dm), dev); L.cast_bf16(W[f"l{i}.w1"], w13[:I]); L.cast_bf16(W[f"l{i}.w3"], w13[I:])
+            # gate/up rows interleaved in 64-row blocks so one GEMM tile holds matching gate and up
+            # columns and the SwiGLU product is formed in its epilogue
+            w13 = _bf16((2 * I, dm), dev)
+            w13v = w13.view(I // 64, 2, 64, dm)
+            w13v[:, 0].copy_(W[f"l{i}.w1"].detach().view(I // 64, 64, dm)); w13v[:, 1].copy_(W[f"l{i}.w3"].detach().view(I // 64, 64, dm))
             w2 = _bf16((dm, I), dev); L.cast_bf16(W[f"l{i}.w2"], w2)
             wq.append((qkv_w, o_w, w13, w2))
         sv["wq"] = wq
@@ -231,8 +237,7 @@ class _ClozeStep(torch.autograd.Function):
             xn = _bf16((T, dm), dev); r1 = _f32((T,), dev)
             L.rmsnorm_fwd(x, W[f"l{i}.san"], xn, None, r1)
             qkv = _bf16((T, QKV), dev)
-            L.gemm(xn, qkv_w, qkv, T, QKV, dm)
-            L.rope(qkv, H + G, 2 * S, cos, sin)
+            L.gemm(xn, qkv_w, qkv, T, QKV, dm, epilogue=L.EPI_ROPE, rope=dict(cos=cos, sin=sin, cols=(H + G) * 64, row_len=2 * S))
             ao = _bf16((T, H * 64), dev); lse = _f32((H, T), dev)
             at = L.attn_args(qkv, H, G, B, 2 * S, tm_tok, seg_s, seg_e)
             L.attn_fwd(at, ao, lse)
@@ -240,10 +245,8 @@ class _ClozeStep(torch.autograd.Function):
             L.gemm(ao, o_w, h, T, dm, H * 64, epilogue=L.EPI_RESID, resid=x)
             hn = _bf16((T, dm), dev); r2 = _f32((T,), dev)
             L.rmsnorm_fwd(h, W[f"l{i}.mln"], hn, None, r2)
-            gu = _bf16((T, 2 * I), dev)
-            L.gemm(hn, w13, gu, T, 2 * I, dm)
-            act = _bf16((T, I), dev)
-            L.swiglu_fwd(gu, act)
+            gu = _bf16((T, 2 * I), dev); act = _bf16((T, I), dev)
+            L.gemm(hn, w13, gu, T, 2 * I, dm, epilogue=L.EPI_SWIGLU, aux=act, ldaux=I)
             xo = _f32((T, dm), dev)
             L.gemm(act, w2, xo, T, dm, I, epilogue=L.EPI_RESID, resid=h)
             layers.append((x, xn, r1, qkv, ao, lse, h, hn, r2, gu, act))
@@ -257,6 +260,8 @@ class _ClozeStep(torch.autograd.Function):
 
         # ---- heads (ref:499-529) ----
         cap = cfg["mask_topk"] * B
+        VP = comm.world() if cfg.get("vocab_parallel") and comm.world() > 1 else 0
+        vrank = comm.rank()
         out = torch.zeros(16, dtype=torch.float32, device=dev)  # [4 losses | 2x4 rating moments(+den)]
         w0_16 = _bf16((dm, dm), dev); L.cast_bf16(W["rh.w0"], w0_16)
         sv["w0_16"] = w0_16
@@ -268,12 +273,33 @@ class _ClozeStep(torch.autograd.Function):
             sel, ws, lab, pos, cnt = L.select_rows(d[f"{m}.watch.weight"].reshape(-1), d[f"{m}.watch.label"].reshape(-1),
                                                    d[f"{m}.watch.position"].reshape(-1).to(torch.int32), cap)
             hs = _bf16((cap, dm), dev); L.gather_rows_bf16(hidden, sel, 0, hs)
-            nb = L.ce_nblocks(K_m)
-            pmax = _f32((nb, cap), dev); psum = _f32((nb, cap), dev); tgt = torch.zeros(cap, dtype=torch.float32, device=dev)
-            L.gemm(hs, table16[lo:hi], None, cap, K_m, dm, epilogue=L.EPI_CE_PARTIAL,
-                   ce=dict(pmax=pmax, psum=psum, tgt=tgt, target=pos))
             lse_r = _f32((cap,), dev); coef = _f32((cap,), dev); term = _f32((cap,), dev)
-            L.ce_finish(pmax, psum, nb, tgt, lab, ws, lse_r, coef, term, out[2 * m:2 * m + 1])
+            vp = None
+            if not VP:
+                nb = L.ce_nblocks(K_m)
+                pmax = _f32((nb, cap), dev); psum = _f32((nb, cap), dev); tgt = torch.zeros(cap, dtype=torch.float32, device=dev)
+                # only the row blocks holding masked rows are computed: the count stays on the device
+                L.gemm(hs, table16[lo:hi], None, cap, K_m, dm, epilogue=L.EPI_CE_PARTIAL,
+                       ce=dict(pmax=pmax, psum=psum, tgt=tgt, target=pos), m_count=cnt)
+                L.ce_finish(pmax, psum, nb, tgt, lab, ws, lse_r, coef, term, out[2 * m:2 * m + 1])
+            else:
+                # vocab-parallel catalog (SURVEY.md 8e / BASELINE config 4): this rank scores EVERY rank's
+                # masked rows against its own slice of the medium's catalog; ranks then exchange
+                # (max, sum exp, target logit) per row - 12 bytes instead of K_m logits
+                R = VP * cap
+                s0, s1 = lo + (K_m * vrank) // VP, lo + (K_m * (vrank + 1)) // VP
+                hs_all = comm.all_gather_rows(hs)
+                pos_loc = comm.all_gather_rows(pos) - (s0 - lo)  # targets outside [0, s1-s0) never match a column
+                nb = L.ce_nblocks(s1 - s0)
+                pmax = _f32((nb, R), dev); psum = _f32((nb, R), dev)
+                st = torch.zeros((3, R), dtype=torch.float32, device=dev)
+                L.gemm(hs_all, table16[s0:s1], None, R, s1 - s0, dm, epilogue=L.EPI_CE_PARTIAL,
+                       ce=dict(pmax=pmax, psum=psum, tgt=st[2], target=pos_loc))
+                L.ce_merge_partials(pmax, psum, nb, st[0], st[1])
+                got = comm.all_to_all_rows(st.view(3, VP, cap).permute(1, 0, 2).contiguous())  # [shard, 3, my rows]
+                L.ce_finish(got[:, 0].contiguous(), got[:, 1].contiguous(), VP, got[:, 2].sum(0), lab, ws, lse_r, coef, term,
+                            out[2 * m:2 * m + 1])
+                vp = dict(hs_all=hs_all, pos_loc=pos_loc, s0=s0, s1=s1)
             # rating: Linear -> GELU -> Linear(d,1), weighted MSE / moments
             rsel, rws, rlab, _rpos, _rc = L.select_rows(d[f"{m}.rating.weight"].reshape(-1), d[f"{m}.rating.label"].reshape(-1),
                                                         d[f"{m}.rating.position"].reshape(-1).to(torch.int32), cap)
@@ -283,7 +309,7 @@ class _ClozeStep(torch.autograd.Function):
             pred = _f32((cap,), dev)
             loss4 = out[4 + 4 * m: 8 + 4 * m]
             L.rating_tail(h1, W["rh.w2"], W["rh.b2"], rlab, rws, cfg["rating_mean"], pred, loss4)
-            heads.append(dict(lo=lo, hi=hi, sel=sel, hs=hs, pos=pos, lse=lse_r, coef=coef, rsel=rsel, rhs=rhs, h1=h1, pre=pre,
+            heads.append(dict(lo=lo, hi=hi, sel=sel, hs=hs, pos=pos, lse=lse_r, coef=coef, cnt=cnt, vp=vp, rsel=rsel, rhs=rhs, h1=h1, pre=pre,
                               pred=pred, rlab=rlab, rws=rws))
         out[1] = out[4]  # train MSE = first moment
         out[3] = out[8]
@@ -324,19 +350,30 @@ class _ClozeStep(torch.autograd.Function):
             K_m = hi - lo
             # ---- watch head backward: recompute logits chunk-wise, never store [rows x catalog] ----
             coef = hd["coef"].clone(); L.scale_by_scalar(coef, gout[2 * m])
-            dhs = _f32((cap, dm), dev)
-            dlog = _bf16((cap, CH), dev)
-            for c0 in range(0, K_m, CH):
-                cn = min(CH, K_m - c0)
-                items = table16[lo + c0: lo + c0 + cn]
-                L.gemm(hd["hs"], items, dlog, cap, cn, dm, ldc=CH, epilogue=L.EPI_CE_GRAD,
-                       ce=dict(lse=hd["lse"], coef=coef, target=hd["pos"]), n_offset=c0)
+            if hd["vp"] is None:
+                rows_n, hs_rows, tgt_rows, lse_rows, coef_rows = cap, hd["hs"], hd["pos"], hd["lse"], coef
+                c_lo, c_hi, lim = lo, hi, hd["cnt"]
+            else:  # vocab-parallel: all ranks' rows against this rank's catalog slice
+                vp = hd["vp"]
+                rows_n, hs_rows, tgt_rows = vp["hs_all"].shape[0], vp["hs_all"], vp["pos_loc"]
+                lse_rows, coef_rows = comm.all_gather_rows(hd["lse"]), comm.all_gather_rows(coef)
+                c_lo, c_hi, lim = vp["s0"], vp["s1"], None
+                dtable[lo:c_lo].zero_(); dtable[c_hi:hi].zero_()  # other slices: their owners write them
+            dhs = _f32((rows_n, dm), dev)
+            dlog = _bf16((rows_n, CH), dev)
+            for c0 in range(0, c_hi - c_lo, CH):
+                cn = min(CH, c_hi - c_lo - c0)
+                items = table16[c_lo + c0: c_lo + c0 + cn]
+                L.gemm(hs_rows, items, dlog, rows_n, cn, dm, ldc=CH, epilogue=L.EPI_CE_GRAD,
+                       ce=dict(lse=lse_rows, coef=coef_rows, target=tgt_rows), n_offset=c0, m_count=lim)
                 # d hidden rows += dlogits . items
-                L.gemm(dlog, items, dhs, cap, dm, cn, lda=CH, b_kmajor=False, ldb=dm,
-                       epilogue=L.EPI_F32 if c0 == 0 else L.EPI_F32_ACCUM)
+                L.gemm(dlog, items, dhs, rows_n, dm, cn, lda=CH, b_kmajor=False, ldb=dm,
+                       epilogue=L.EPI_F32 if c0 == 0 else L.EPI_F32_ACCUM, m_count=lim)
                 # d table rows = dlogits^T . hidden rows
-                L.gemm(dlog, hd["hs"], dtable[lo + c0: lo + c0 + cn], cn, dm, cap, a_kmajor=False, lda=CH, b_kmajor=False,
-                       ldb=dm, epilogue=L.EPI_F32, split_k=-1)
+                L.gemm(dlog, hs_rows, dtable[c_lo + c0: c_lo + c0 + cn], cn, dm, rows_n, a_kmajor=False, lda=CH, b_kmajor=False,
+                       ldb=dm, epilogue=L.EPI_F32, split_k=-1, k_count=lim)
+            if hd["vp"] is not None:
+                dhs = comm.reduce_scatter_rows(dhs)  # sum of the shards' partial d(hidden rows), my rows only
             L.scatter_rows_f32(dhs, hd["sel"], 0, dhid)
             # ---- rating head backward ----
             dpre = _bf16((cap, dm), dev); dp = _f32((cap,), dev)
@@ -370,7 +407,7 @@ class _ClozeStep(torch.autograd.Function):
             g_w2 = _f32((dm, I), dev)
             L.gemm(dx16, act, g_w2, dm, I, T, a_kmajor=False, lda=dm, b_kmajor=False, ldb=I, epilogue=L.EPI_F32, split_k=-1)
             dgu = _bf16((T, 2 * I), dev)
-            L.swiglu_bwd(gu, dact, dgu)
+            L.swiglu_bwd(gu, dact, dgu, interleaved64=True)
             del dact
             dhn = _bf16((T, dm), dev)
             L.gemm(dgu, w13, dhn, T, dm, 2 * I, b_kmajor=False, ldb=dm)
@@ -395,7 +432,8 @@ class _ClozeStep(torch.autograd.Function):
             g_san = _f32((dm,), dev)
             L.rmsnorm_bwd(x, W[f"l{i}.san"], r1, dxn, None, dh, dx, dx16, g_san)
             G_[f"l{i}.q"], G_[f"l{i}.k"], G_[f"l{i}.v"] = g_qkv[: H * 64], g_qkv[H * 64:(H + G) * 64], g_qkv[(H + G) * 64:]
-            G_[f"l{i}.o"], G_[f"l{i}.w1"], G_[f"l{i}.w3"], G_[f"l{i}.w2"] = g_o, g_w13[:I], g_w13[I:], g_w2
+            g13 = g_w13.view(I // 64, 2, 64, dm)  # rows are in the interleaved gate/up block order
+            G_[f"l{i}.o"], G_[f"l{i}.w1"], G_[f"l{i}.w3"], G_[f"l{i}.w2"] = g_o, g13[:, 0].reshape(I, dm), g13[:, 1].reshape(I, dm), g_w2
             G_[f"l{i}.san"], G_[f"l{i}.mln"] = g_san, g_mln
             sv["layers"][i] = None  # free this layer's activations
 

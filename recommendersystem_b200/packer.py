@@ -57,3 +57,64 @@ def concat(per_user, batch_size):
     n = sum(len(u["userid"]) for u in per_user)
     total = n + (-n) % batch_size
     return {k: L.concat_pad_host([u[k] for u in per_user], total) for k in per_user[0]}
+
+
+# ------------------------------------------------------------------------------
+# per-user featuriser: transformer.jl:79-142 `get_data` (+ history_tools.jl:37-75)
+# ------------------------------------------------------------------------------
+PLANNED_STATUS = 5                        # transformer.jl:18
+PACK_METRICS = ("watch", "rating", "status")  # transformer.jl:17
+
+
+def _columns(items):
+    """List of msgpack item dicts -> struct of arrays (None -> NaN for the history_* fields)."""
+    n = len(items)
+    col = lambda k, dt: np.fromiter((x[k] for x in items), dtype=dt, count=n)  # noqa: E731
+    opt = lambda k: np.fromiter((np.nan if x[k] is None else x[k] for x in items), dtype=np.float64, count=n)  # noqa: E731
+    return dict(medium=col("medium", np.int32), matchedid=col("matchedid", np.int32), ts=col("history_max_ts", np.float64),
+                status=col("status", np.int32), rating=col("rating", np.float32), progress=col("progress", np.float32),
+                h_status=opt("history_status"), h_rating=opt("history_rating"))
+
+
+def get_data(data, userid, num_items0):
+    """Columnar restatement of the Julia packer's per-user step: `tokenize!` (collapse runs of
+    one (medium, matchedid): first event's fields, last event's status/rating/progress),
+    `project!` (drop events that change neither status nor rating), then the 9 feature and 18
+    target vectors with the reference's dtypes.  No per-item Python after the column build."""
+    c = _columns(data["items"])
+    n0 = len(c["medium"])
+    if n0:
+        key = c["medium"].astype(np.int64) << 32 | c["matchedid"].astype(np.int64)
+        start = np.flatnonzero(np.r_[True, key[1:] != key[:-1]])       # first event of each span
+        last = np.r_[start[1:], n0] - 1                                 # last event of each span
+    else:
+        start = last = np.zeros(0, np.int64)
+    medium, mid, ts = c["medium"][start], c["matchedid"][start], c["ts"][start]
+    h_status, h_rating = c["h_status"][start], c["h_rating"][start]
+    status, rating, progress = c["status"][last], c["rating"][last], c["progress"][last]
+    keep = ~((h_status == status) & (h_rating == rating))               # NaN (nothing) never equals: kept
+    medium, mid, ts, h_status, h_rating = medium[keep], mid[keep], ts[keep], h_status[keep], h_rating[keep]
+    status, rating, progress = status[keep], rating[keep], progress[keep]
+    n = len(mid)
+    u = data["user"]
+    d = {
+        "userid": np.full(n, userid, np.int32), "token_mask_ids": np.zeros(n, np.int32), "time": ts.astype(np.float64),
+        "gender": np.full(n, 0 if u["gender"] is None else u["gender"] + 1, np.int32),
+        "source": np.full(n, u["source"], np.int32),
+        "matchedid": (mid + np.where(medium == 1, num_items0, 0)).astype(np.int32),
+        "status": status.astype(np.int32), "rating": rating.astype(np.float32), "progress": progress.astype(np.float32),
+    }
+    no_hist = np.isnan(h_status)
+    watch = ((status == 0) & no_hist) | ((status > PLANNED_STATUS) & (no_hist | ((h_status > 0) & (h_status <= PLANNED_STATUS))))
+    rated = (rating > 0) & ~(rating == h_rating)
+    stat = (status > 0) & ~(status == h_status)
+    d["token_mask_ids"] = rated.astype(np.int32)
+    labels = {"watch": np.ones(n, np.float32), "rating": rating.astype(np.float32), "status": status.astype(np.float32)}
+    hits = {"watch": watch, "rating": rated, "status": stat}
+    for m in (0, 1):
+        for metric in PACK_METRICS:
+            h = hits[metric] & (medium == m)
+            d[f"{m}.{metric}.label"] = np.where(h, labels[metric], 0).astype(np.float32)
+            d[f"{m}.{metric}.weight"] = h.astype(np.float32)
+            d[f"{m}.{metric}.position"] = np.where(h, mid, 0).astype(np.int32)
+    return d

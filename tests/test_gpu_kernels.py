@@ -95,6 +95,78 @@ def test_gemm_epilogues():
     report("table", o, res + pre_ref.float(), 1e-3)
 
 
+def test_gemm_fused_swiglu_and_rope_epilogues():
+    """The fused epilogues must reproduce the stand-alone kernels bit for bit."""
+    M, K, I = 392, 192, 320
+    A = g_randn(M, K, seed=21).bfloat16()
+    w1 = g_randn(I, K, seed=22, scale=0.2).bfloat16()
+    w3 = g_randn(I, K, seed=23, scale=0.2).bfloat16()
+    # reference: plain GEMM to [gate | up], stand-alone swiglu kernel
+    gu_ref = torch.empty(M, 2 * I, device=DEV, dtype=torch.bfloat16)
+    L.gemm(A, torch.cat([w1, w3]).contiguous(), gu_ref, M, 2 * I, K)
+    act_ref = torch.empty(M, I, device=DEV, dtype=torch.bfloat16)
+    L.swiglu_fwd(gu_ref, act_ref)
+    w13 = torch.stack([w1.view(I // 64, 64, K), w3.view(I // 64, 64, K)], 1).reshape(2 * I, K).contiguous()
+    gu = torch.empty(M, 2 * I, device=DEV, dtype=torch.bfloat16)
+    act = torch.full((M, I), float("nan"), device=DEV, dtype=torch.bfloat16)
+    L.gemm(A, w13, gu, M, 2 * I, K, epilogue=L.EPI_SWIGLU, aux=act, ldaux=I)
+    guv = gu.view(M, I // 64, 2, 64)
+    assert torch.equal(guv[:, :, 0].reshape(M, I), gu_ref[:, :I]) and torch.equal(guv[:, :, 1].reshape(M, I), gu_ref[:, I:])
+    assert torch.equal(act, act_ref)
+    # backward kernel in the interleaved layout == old layout, re-ordered
+    dact = g_randn(M, I, seed=24).bfloat16()
+    dgu_ref = torch.empty_like(gu_ref); L.swiglu_bwd(gu_ref, dact, dgu_ref)
+    dgu = torch.empty_like(gu); L.swiglu_bwd(gu, dact, dgu, interleaved64=True)
+    dv = dgu.view(M, I // 64, 2, 64)
+    assert torch.equal(dv[:, :, 0].reshape(M, I), dgu_ref[:, :I]) and torch.equal(dv[:, :, 1].reshape(M, I), dgu_ref[:, I:])
+    # RoPE epilogue: q,k heads rotated, v heads untouched
+    rows, row_len, H, G = 2, 256, 3, 1
+    T, N = rows * row_len, (H + 2 * G) * 64
+    X = g_randn(T, K, seed=25).bfloat16()
+    Wq = g_randn(N, K, seed=26, scale=0.2).bfloat16()
+    inv = 1.0 / (500000.0 ** (torch.arange(0, 64, 2).float() / 64))
+    ang = torch.outer(torch.arange(row_len).float(), inv)
+    cos, sin = torch.cos(ang).to(DEV).contiguous(), torch.sin(ang).to(DEV).contiguous()
+    ref = torch.empty(T, N, device=DEV, dtype=torch.bfloat16)
+    L.gemm(X, Wq, ref, T, N, K)
+    L.rope(ref, H + G, row_len, cos, sin)
+    got = torch.empty(T, N, device=DEV, dtype=torch.bfloat16)
+    L.gemm(X, Wq, got, T, N, K, epilogue=L.EPI_ROPE, rope=dict(cos=cos, sin=sin, cols=(H + G) * 64, row_len=row_len))
+    assert torch.equal(got, ref)
+    pos = torch.randint(0, row_len, (T,), generator=torch.Generator().manual_seed(3)).int().to(DEV)
+    L.gemm(X, Wq, ref, T, N, K); L.rope(ref, H + G, row_len, cos, sin, pos=pos)
+    L.gemm(X, Wq, got, T, N, K, epilogue=L.EPI_ROPE, rope=dict(cos=cos, sin=sin, cols=(H + G) * 64, pos=pos))
+    assert torch.equal(got, ref)
+
+
+def test_gemm_device_side_limits():
+    """m_count / k_count (the heads' masked-row count, read on the device): rows beyond the
+    rounded count stay untouched, the K range is cut, empty split-K slices contribute zero."""
+    M, N, K = 640, 384, 256
+    A = g_randn(M, K, seed=11).bfloat16()
+    B = g_randn(N, K, seed=12).bfloat16()
+    ref = A.float() @ B.float().t()
+    for count in (0, 1, 128, 200, 640, 9999):
+        cnt = torch.tensor([count], dtype=torch.int32, device=DEV)
+        out = torch.full((M, N), -7.0, device=DEV)
+        L.gemm(A, B, out, M, N, K, epilogue=L.EPI_F32, m_count=cnt)
+        lim = min(M, (count + 127) // 128 * 128)
+        report(f"m_count {count}", out[:lim], ref[:lim], 1e-5) if lim else None
+        assert bool((out[lim:] == -7.0).all())
+    # K limit: C = A[:lim]^T B[:lim] with the operands stored [K, M] and [K, N]
+    Kd = 1024
+    At = g_randn(Kd, 256, seed=13).bfloat16()
+    Bt = g_randn(Kd, 384, seed=14).bfloat16()
+    for count, sk in ((0, 0), (130, 0), (300, 4), (5, 4), (1024, 4), (4000, -1)):
+        cnt = torch.tensor([count], dtype=torch.int32, device=DEV)
+        lim = min(Kd, (count + 127) // 128 * 128)
+        ref2 = At[:lim].float().t() @ Bt[:lim].float()
+        out = torch.full((256, 384), float("nan"), device=DEV)
+        L.gemm(At, Bt, out, 256, 384, Kd, a_kmajor=False, b_kmajor=False, epilogue=L.EPI_F32, split_k=sk, k_count=cnt)
+        assert bool(torch.isfinite(out).all()), count
+        assert float((out - ref2).abs().max()) <= 1e-5 * max(1.0, float(ref2.abs().max())), (count, sk)
+
+
 def test_gemm_fused_cross_entropy():
     M, N, K = 200, 1000, 128   # rows, catalog, dim
     h = g_randn(M, K, seed=9).bfloat16()
@@ -111,7 +183,9 @@ def test_gemm_fused_cross_entropy():
     lse = torch.empty(M, device=DEV); coef = torch.empty(M, device=DEV); term = torch.empty(M, device=DEV)
     loss = torch.zeros(1, device=DEV)
     L.ce_finish(pmax, psum, nb, tgt, label, w, lse, coef, term, loss)
-    report("lse", lse, torch.logsumexp(logits, 1), 1e-5)
+    live = w > 0  # weightless (padding) rows report lse 0: they may lie beyond the GEMM's row limit
+    report("lse", lse[live], torch.logsumexp(logits, 1)[live], 1e-5)
+    assert bool((lse[~live] == 0).all())
     assert abs(float(loss) - float(loss_ref)) < 1e-4 * abs(float(loss_ref)), (float(loss), float(loss_ref))
     # backward chunk: dlogits = coef * (softmax - onehot)
     c0, cn = 256, 512
