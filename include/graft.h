@@ -224,6 +224,9 @@ int graft_ce_merge_partials(const float* pmax, const float* psum, int n_blocks, 
  * train MSE) and loss4[3] = max(sum w, 1e-8) */
 int graft_rating_tail(const void* h1_bf16, int d, const float* w2, const float* b2, int cap, const float* label_sel,
                       const float* w_sel, float rating_mean, float* pred_out, float* loss4, graft_stream_t stream);
+/* ranking inference, transformer.model.py:535-536: pred[m] = bf16(h1[m,:] . w2 + b2) for every token row */
+int graft_rating_pred(const void* h1_bf16, int d, const float* w2, const float* b2, int64_t rows, float* pred_out,
+                      graft_stream_t stream);
 /* backward of rating tail + GELU: dpre bf16 [cap,d], dw2[d], db2[1] (overwritten);
  * gscale = device scalar dL/dloss; dp_scratch [cap] */
 int graft_rating_tail_bwd(const void* pre_bf16, const void* h1_bf16, int d, const float* w2, int cap,

@@ -142,10 +142,13 @@ def rope_tables(head_dim, n, theta=500000.0):
 
 
 def rope(x, cos, sin):
-    """transformer.model.py:182-190; x [B,T,H,hd], pair-interleaved rotation."""
+    """transformer.model.py:182-190; x [B,T,H,hd], pair-interleaved rotation.  cos/sin are
+    [T, hd/2] (row positions) or [B, T, hd/2] (gathered by rope_input_pos, :336-339)."""
     xf = x.float().reshape(*x.shape[:-1], -1, 2)
     a, b = xf[..., 0], xf[..., 1]
-    c, s = cos[None, :, None, :].float(), sin[None, :, None, :].float()
+    if cos.dim() == 2:
+        cos, sin = cos[None], sin[None]
+    c, s = cos[:, :, None, :].float(), sin[:, :, None, :].float()
     return torch.stack((a * c - b * s, a * s + b * c), dim=-1).flatten(3).type_as(x)
 
 
@@ -179,7 +182,7 @@ def trunk(x, p, config, vis, positions=None, taps=None):
     if positions is None:
         cos, sin = cos[:T], sin[:T]
     else:
-        raise NotImplementedError("oracle: rope_input_pos (inference) not restated yet")
+        cos, sin = cos[positions.long()], sin[positions.long()]  # [B, T, hd/2]
     for i in range(config["num_layers"]):
         pre = f"transformers.layers.{i}."
         x = x + attention(rms_norm(x, p[pre + "sa_norm.scale"]), p, pre + "attn.", config, vis, cos, sin)
@@ -237,6 +240,23 @@ def step(d, p, config, randval, evaluate=False, taps=None):
     if taps is not None:
         taps["hidden"] = hidden
     return cloze_losses(hidden, dm, p, config, evaluate), dm
+
+
+def inference_forward(d, p, config, task):
+    """transformer.model.py:531-538 + 464-491: d holds [U, S'] arrays; `rope_input_pos`
+    (optional) gives the RoPE position of each history position (tokens 2p, 2p+1)."""
+    x0 = embed_tokens(d, p, config)
+    vis = visibility(d["userid"], d["token_mask_ids"])
+    pos = None
+    if "rope_input_pos" in d:
+        rp = d["rope_input_pos"]
+        pos = torch.stack((2 * rp, 2 * rp + 1), dim=2).reshape(rp.shape[0], -1)
+    e = trunk(x0, p, config, vis, positions=pos)
+    if task == "retrieval":
+        return e
+    assert task == "ranking"
+    h = F.gelu(F.linear(e, p["rating_head.0.weight"], p["rating_head.0.bias"]))
+    return F.linear(h, p["rating_head.2.weight"], p["rating_head.2.bias"])
 
 
 def step_with_grads(d, p, config, randval, task_weights, autocast=False):

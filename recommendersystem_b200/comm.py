@@ -37,8 +37,8 @@ def all_gather_rows(t, group=None):
         dist.all_gather_into_tensor(out, t, group=group)
         return out
     host = t.cpu()
-    if host.dtype == torch.bfloat16:  # gloo has no bf16: move the raw 16-bit patterns
-        host = host.view(torch.int16)
+    if host.dtype == torch.bfloat16:  # gloo has no bf16: move the raw bytes
+        host = host.view(torch.uint8)
     parts = [torch.empty_like(host) for _ in range(P)]
     dist.all_gather(parts, host, group=group)
     cat = torch.cat(parts, 0)

@@ -368,6 +368,11 @@ def rating_tail(h1, w2, b2, lab, w, mean, pred, loss4):
            "graft_rating_tail")
 
 
+def rating_pred(h1, w2, b2, pred):
+    rows, d = h1.shape
+    _check(load().graft_rating_pred(ptr(h1), d, ptr(w2), ptr(b2), i64(rows), ptr(pred), stream()), "graft_rating_pred")
+
+
 def rating_tail_bwd(pre, h1, w2, lab, w, mean, pred, loss4, gscale, dpre, dp, dw2, db2):
     cap, d = h1.shape
     _check(load().graft_rating_tail_bwd(ptr(pre), ptr(h1), d, ptr(w2), cap, ptr(lab), ptr(w), f32(mean), ptr(pred), ptr(loss4),

@@ -224,6 +224,7 @@ class _ClozeStep(torch.autograd.Function):
         feats = _f32((N, 32), dev)
         L.action_embed(aa, x, feats)
         sv["feats"], sv["aa"], sv["mid"] = feats, aa, mid
+        sv["batch"] = d  # `aa` holds raw device pointers into the batch: keep its tensors alive until backward
 
         tm_tok = torch.empty(T, dtype=torch.int32, device=dev); L.interleave_i32(d["token_mask_ids"].reshape(-1), tm_tok)
         seg_s, seg_e = L.token_segments(d["userid"])
@@ -460,6 +461,55 @@ class _ClozeStep(torch.autograd.Function):
         return (None, None, None, *grads)
 
 
+# ------------------------------------------------------------------------------
+@torch.no_grad()
+def _inference_hidden(model, d):
+    """ref:464-491 + 335-343 without autograd state: `d` holds [U, S'] arrays incl. optional
+    `rope_input_pos` (ref:470-476) and arbitrary `token_mask_ids` (embed.py:122-125).  Returns the
+    final-norm output [U, 2S', d] fp32.  Same kernels as the train forward; nothing is kept."""
+    cfg, P = model.config, model._params
+    W = dict(zip(P.names, P.tensors))
+    dev = W["ie.id"].device
+    if dev.type != "cuda":
+        raise L.GraftError("the inference forward has no CPU path: move the model and batch to a CUDA device")
+    B, S = d["userid"].shape
+    N, T = B * S, 2 * B * S
+    dm, H, G, I = cfg["embed_dim"], cfg["num_heads"], cfg["num_kv_heads"], cfg["intermediate_dim"]
+    assert dm // H == 64 and I % 64 == 0 and (2 * S) % 128 == 0, "head_dim 64, FFN % 64, row length % 64 positions"
+    QKV = (H + 2 * G) * 64
+    d = {k: (v if v.is_contiguous() else v.contiguous()) for k, v in d.items()}
+    wts = model._inference_weights()
+    table = wts["table"]
+    x = _f32((T, dm), dev)
+    L.item_gather(table, d["matchedid"].reshape(-1), x)
+    L.action_embed(model._action_args(d, W, N), x, _f32((N, 32), dev))
+    tm_tok = torch.empty(T, dtype=torch.int32, device=dev); L.interleave_i32(d["token_mask_ids"].reshape(-1), tm_tok)
+    seg_s, seg_e = L.token_segments(d["userid"])
+    cos, sin = model.transformers.freqs_cos, model.transformers.freqs_sin
+    rope = dict(cos=cos, sin=sin, cols=(H + G) * 64, row_len=2 * S)
+    if "rope_input_pos" in d:  # ref:470-474: token positions 2p (item) and 2p+1 (action)
+        rp = d["rope_input_pos"].reshape(-1).to(torch.int32)
+        rope["pos"] = torch.stack((2 * rp, 2 * rp + 1), dim=1).reshape(-1).contiguous()
+        assert int(cos.shape[0]) >= 2, "rope table missing"
+    else:
+        assert 2 * S <= cos.shape[0], "row longer than the RoPE table (2 * max_sequence_length)"
+    xn = _bf16((T, dm), dev); qkv = _bf16((T, QKV), dev); ao = _bf16((T, H * 64), dev); lse = _f32((H, T), dev)
+    gu = _bf16((T, 2 * I), dev); act = _bf16((T, I), dev)
+    for i in range(cfg["num_layers"]):
+        qkv_w, o_w, w13, w2 = wts["layers"][i]
+        L.rmsnorm_fwd(x, W[f"l{i}.san"], xn, None, None)
+        L.gemm(xn, qkv_w, qkv, T, QKV, dm, epilogue=L.EPI_ROPE, rope=rope)
+        L.attn_fwd(L.attn_args(qkv, H, G, B, 2 * S, tm_tok, seg_s, seg_e), ao, lse)
+        h = _f32((T, dm), dev)
+        L.gemm(ao, o_w, h, T, dm, H * 64, epilogue=L.EPI_RESID, resid=x)
+        L.rmsnorm_fwd(h, W[f"l{i}.mln"], xn, None, None)
+        L.gemm(xn, w13, gu, T, 2 * I, dm, epilogue=L.EPI_SWIGLU, aux=act, ldaux=I)
+        L.gemm(act, w2, x, T, dm, I, epilogue=L.EPI_RESID, resid=h)
+    hidden = _f32((T, dm), dev)
+    L.rmsnorm_fwd(x, W["norm"], None, hidden, None)
+    return hidden.view(B, 2 * S, dm)
+
+
 class RecommenderModel(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -477,10 +527,13 @@ class RecommenderModel(nn.Module):
         self._meta_cache = None
         self._taps = None
         self.mask_rand = None  # tests may inject f(shape, device) -> randval
+        self._infer_cache = None
         if config["forward"] == "train":
             self.forward = self.train_forward
+        elif config["forward"] == "inference":
+            self.forward = self.inference_forward
         else:
-            raise NotImplementedError("inference forward is not built yet (SURVEY.md 8f rank 3)")
+            raise AssertionError(config["forward"])
 
     # ref:379-389, with the matrix passed in or read from <datadir>/media_embeddings.h5
     def load_pretrained_embeddings(self, datadir=None, metadata=None):
@@ -506,6 +559,64 @@ class RecommenderModel(nn.Module):
             L.cast_pad_rows(w.detach(), buf)
             self._meta_cache = (key, buf, Mp)
         return self._meta_cache[1], self._meta_cache[2]
+
+    def _inference_weights(self):
+        """bf16 operand copies of the block weights and the fused item table (= ItemEmbedding.fuse(),
+        ref:120-133), rebuilt only when a parameter changed (inference weights are static)."""
+        P = self._params
+        key = tuple((t.data_ptr(), t._version) for t in P.tensors) + (str(P.tensors[0].device),)
+        if self._infer_cache is not None and self._infer_cache[0] == key:
+            return self._infer_cache[1]
+        cfg = self.config
+        W = dict(zip(P.names, P.tensors))
+        dev = W["ie.id"].device
+        dm, H, G, I = cfg["embed_dim"], cfg["num_heads"], cfg["num_kv_heads"], cfg["intermediate_dim"]
+        QKV = (H + 2 * G) * 64
+        layers = []
+        for i in range(cfg["num_layers"]):
+            qkv_w = _bf16((QKV, dm), dev)
+            L.cast_bf16(W[f"l{i}.q"], qkv_w[: H * 64]); L.cast_bf16(W[f"l{i}.k"], qkv_w[H * 64:(H + G) * 64])
+            L.cast_bf16(W[f"l{i}.v"], qkv_w[(H + G) * 64:])
+            o_w = _bf16((dm, H * 64), dev); L.cast_bf16(W[f"l{i}.o"], o_w)
+            w13 = _bf16((2 * I, dm), dev)
+            w13v = w13.view(I // 64, 2, 64, dm)
+            w13v[:, 0].copy_(W[f"l{i}.w1"].detach().view(I // 64, 64, dm)); w13v[:, 1].copy_(W[f"l{i}.w3"].detach().view(I // 64, 64, dm))
+            w2 = _bf16((dm, I), dev); L.cast_bf16(W[f"l{i}.w2"], w2)
+            layers.append((qkv_w, o_w, w13, w2))
+        meta16, Mp = self._meta_bf16()
+        pw16 = _bf16((dm, Mp), dev); L.cast_pad_rows(W["ie.pw"].detach(), pw16)
+        Vt1 = W["ie.id"].shape[0]
+        table = _f32((Vt1, dm), dev)
+        L.gemm(meta16, pw16, table, Vt1, dm, Mp, epilogue=L.EPI_TABLE, resid=W["ie.id"].detach(), bias=W["ie.pb"].detach())
+        w0_16 = _bf16((dm, dm), dev); L.cast_bf16(W["rh.w0"], w0_16)
+        out = dict(layers=layers, table=table, w0_16=w0_16)
+        self._infer_cache = (key, out)
+        return out
+
+    def fused_item_table(self):
+        """ItemEmbedding.fuse() (ref:120-133): id rows + projected metadata rows, [V+1, d] fp32.
+        What register.py:14-38 exports and what the tied head scores against."""
+        return self._inference_weights()["table"]
+
+    @torch.compiler.disable
+    def inference_forward(self, d, task):
+        """ref:531-538: retrieval -> final-norm token states [U, 2S, d]; ranking -> rating head
+        on every token [U, 2S, 1] (bf16, as the autocast reference returns it)."""
+        hidden = _inference_hidden(self, d)
+        if task == "retrieval":
+            return hidden
+        if task != "ranking":
+            raise AssertionError(task)
+        U, T2, dm = hidden.shape
+        W = dict(zip(self._params.names, self._params.tensors))
+        dev = hidden.device
+        rows = U * T2
+        x16 = _bf16((rows, dm), dev); L.cast_bf16(hidden.view(rows, dm), x16)
+        h1 = _bf16((rows, dm), dev); pre = _bf16((rows, dm), dev)
+        L.gemm(x16, self._inference_weights()["w0_16"], h1, rows, dm, dm, epilogue=L.EPI_BIAS_GELU, bias=W["rh.b0"], aux=pre)
+        pred = _f32((rows,), dev)
+        L.rating_pred(h1, W["rh.w2"], W["rh.b2"], pred)
+        return pred.view(U, T2, 1).to(torch.bfloat16)
 
     def _action_args(self, d, W, N):
         cfg = self.config

@@ -31,33 +31,38 @@ def _free_port():
     return port
 
 
-def _step(g, batch, randval, vocab_parallel):
+def _step(g, batch, randval, vocab_parallel, dev="cuda:0"):
     from recommendersystem_b200.testing import batch_to_device, model_from_params
     cfg = dict(g["config"], vocab_parallel=vocab_parallel)
-    model = model_from_params(cfg, g["param"], "cuda:0")
-    rv = torch.as_tensor(randval).to("cuda:0")
+    model = model_from_params(cfg, g["param"], dev)
+    rv = torch.as_tensor(randval).to(dev)
     model.mask_rand = lambda shape, dev: rv.reshape(shape)
-    losses = model(batch_to_device(batch, "cuda:0"), False)
+    losses = model(batch_to_device(batch, dev), False)
     total = sum(l * w for l, w in zip(losses, g["task_weights"]))
     total.backward()
     grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
     return torch.stack([l.detach() for l in losses]), grads
 
 
-def _worker(rank, world, port, out):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+def _worker(rank, world, port, out, backend="gloo", dev="cuda:0"):
+    if port is not None:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    if backend == "nccl":
+        torch.cuda.set_device(dev)
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from recommendersystem_b200 import synthetic
         g = load_golden()
         cfg, rows = g["config"], g["rows"]
         if rank == 0:
             batch, randval = g["batch"], g["randval"]
-        else:  # a different batch on the other rank: data parallel over users
-            batch = synthetic.make_batches(cfg, rows, 1, seed=77, len_median=20.0, len_clip=(3, 80))[0]
-            randval = np.random.default_rng(5).random((rows, cfg["max_sequence_length"]), dtype=np.float32)
-        l_ref, g_ref = _step(g, batch, randval, False)
-        l_vp, g_vp = _step(g, batch, randval, True)
+        else:  # a different batch on every other rank: data parallel over users
+            batch = synthetic.make_batches(cfg, rows, 1, seed=77 + rank, len_median=20.0, len_clip=(3, 80))[0]
+            randval = np.random.default_rng(5 + rank).random((rows, cfg["max_sequence_length"]), dtype=np.float32)
+        l_ref, g_ref = _step(g, batch, randval, False, dev)
+        l_vp, g_vp = _step(g, batch, randval, True, dev)
         assert torch.allclose(l_vp, l_ref, rtol=2e-5, atol=1e-6), (l_vp, l_ref)
         shared = ("item_embedding.matchedid_embedding.embedding.weight", "item_embedding.projection_layer.weight",
                   "item_embedding.projection_layer.bias")
@@ -65,12 +70,14 @@ def _worker(rank, world, port, out):
         for n in g_ref:
             a, b = g_vp[n].float(), g_ref[n].float()
             if n in shared:  # compare after the optimiser's cross-rank SUM
-                a, b = a.cpu(), b.cpu()
+                if backend != "nccl":
+                    a, b = a.cpu(), b.cpu()
                 dist.all_reduce(a); dist.all_reduce(b)
             rel = float((a - b).norm() / b.norm().clamp_min(1e-20))
             worst = max(worst, rel)
             assert rel < 2e-3, (n, rel)
-        out[rank] = 1
+        if out is not None:
+            out[rank] = 1
         print(f"rank {rank}: losses {l_vp.tolist()} worst grad rel {worst:.2e}")
     finally:
         dist.destroy_process_group()
@@ -88,3 +95,11 @@ def test_vocab_parallel_matches_replicated_world2():
         p.join(300)
         assert p.exitcode == 0
     assert list(out) == [1] * world
+
+
+if __name__ == "__main__":  # torchrun --nproc-per-node N tests/test_gpu_vocab_parallel.py : one rank per GPU over NCCL
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r, w = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    _worker(r, w, None, None, backend="nccl", dev=f"cuda:{int(os.environ.get('LOCAL_RANK', r))}")
+    print(f"rank {r}/{w}: vocab-parallel parity over NCCL ok")

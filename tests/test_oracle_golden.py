@@ -69,3 +69,20 @@ def test_jagged_offsets_and_block_permutation():
     change = np.where(u[:-1] != u[1:])[0] + 1
     blocks = np.split(np.arange(len(u)), change)
     assert np.concatenate([blocks[b] for b in [2, 0, 3, 1]]).tolist() == perm.tolist()
+
+
+def test_inference_forward_matches_reference():
+    """oracle.inference_forward vs the reference module in inference mode (rope_input_pos,
+    per-candidate token_mask_ids): tests/golden/inference_tiny.npz."""
+    import json
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inference_tiny.npz"))
+    cfg = json.loads(bytes(z["config_json"]).decode())
+    p = {k[6:]: torch.as_tensor(z[k]) for k in z.files if k.startswith("param/")}
+    for task in ("retrieval", "ranking"):
+        pre = f"{task}/batch/"
+        d = {k[len(pre):]: torch.as_tensor(z[k]) for k in z.files if k.startswith(pre)}
+        with torch.no_grad():
+            out = oc.inference_forward(d, p, cfg, task).numpy()
+        ref = z[f"{task}/out_fp32"]
+        assert np.abs(out - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), task
