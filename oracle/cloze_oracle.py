@@ -93,8 +93,11 @@ def action_features(d, p, config):
 
 
 def item_table(p, lo=None, hi=None):
-    """transformer.model.py:120-128 / 165-169: id rows + projected metadata rows."""
+    """transformer.model.py:120-128 / 165-169: id rows + projected metadata rows; a fused
+    table (finetune: ItemEmbedding.fuse() at load time, in fp32) is used as is."""
     sl = slice(lo, hi)
+    if "item_embedding.fused_embedding" in p:
+        return p["item_embedding.fused_embedding"][sl]
     return p["item_embedding.matchedid_embedding.embedding.weight"][sl] + F.linear(
         p["item_embedding.metadata_embedding.embedding.weight"][sl],
         p["item_embedding.projection_layer.weight"],
@@ -107,6 +110,10 @@ def embed_tokens(d, p, config):
     then action token per position."""
     act = F.linear(action_features(d, p, config), p["action_embedding.linear.weight"], p["action_embedding.linear.bias"])
     ids = d["matchedid"]
+    if "item_embedding.fused_embedding" in p:  # transformer.model.py:139-142
+        item = _masked_lookup(p["item_embedding.fused_embedding"], ids)
+        B, S, D = item.shape
+        return torch.stack((item, act), dim=2).reshape(B, 2 * S, D)
     item = _masked_lookup(p["item_embedding.matchedid_embedding.embedding.weight"], ids) + F.linear(
         _masked_lookup(p["item_embedding.metadata_embedding.embedding.weight"], ids),
         p["item_embedding.projection_layer.weight"],
@@ -152,14 +159,21 @@ def rope(x, cos, sin):
     return torch.stack((a * c - b * s, a * s + b * c), dim=-1).flatten(3).type_as(x)
 
 
-def attention(x, p, pre, config, vis, cos, sin):
-    """transformer.model.py:256-286 (no LoRA): softmax attention, scale 1/sqrt(hd)."""
+def attention(x, p, pre, config, vis, cos, sin, drop=None):
+    """transformer.model.py:256-286: softmax attention, scale 1/sqrt(hd); in finetune mode
+    LoRA r=8, alpha=16 on q and v (:235-254, 263-271).  `drop` = (mask_q, mask_v) multiplies
+    the LoRA input like nn.Dropout(0.1) in training (masks already scaled by 1/0.9); None = eval."""
     B, T, D = x.shape
     H, G = config["num_heads"], config["num_kv_heads"]
     hd = D // H
-    q = F.linear(x, p[pre + "q_proj.weight"]).view(B, T, H, hd)
+    q = F.linear(x, p[pre + "q_proj.weight"])
     k = F.linear(x, p[pre + "k_proj.weight"]).view(B, T, G, hd)
-    v = F.linear(x, p[pre + "v_proj.weight"]).view(B, T, G, hd)
+    v = F.linear(x, p[pre + "v_proj.weight"])
+    if config.get("finetune"):
+        xq, xv = (x, x) if drop is None else (x * drop[0], x * drop[1])
+        q = q + F.linear(F.linear(xq, p[pre + "q_proj_lora_A.weight"]), p[pre + "q_proj_lora_B.weight"]) * 2.0
+        v = v + F.linear(F.linear(xv, p[pre + "v_proj_lora_A.weight"]), p[pre + "v_proj_lora_B.weight"]) * 2.0
+    q, v = q.view(B, T, H, hd), v.view(B, T, G, hd)
     q, k = rope(q, cos, sin), rope(k, cos, sin)
     o = F.scaled_dot_product_attention(
         q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), attn_mask=vis[:, None], enable_gqa=H != G
@@ -172,7 +186,7 @@ def swiglu(x, p, pre):
     return F.linear(F.silu(F.linear(x, p[pre + "w1.weight"])) * F.linear(x, p[pre + "w3.weight"]), p[pre + "w2.weight"])
 
 
-def trunk(x, p, config, vis, positions=None, taps=None):
+def trunk(x, p, config, vis, positions=None, taps=None, drops=None):
     """transformer.model.py:297-343: pre-norm residual blocks + final norm.
     RoPE positions are token indices inside the row unless given (:336-339)."""
     T = x.shape[1]
@@ -185,7 +199,8 @@ def trunk(x, p, config, vis, positions=None, taps=None):
         cos, sin = cos[positions.long()], sin[positions.long()]  # [B, T, hd/2]
     for i in range(config["num_layers"]):
         pre = f"transformers.layers.{i}."
-        x = x + attention(rms_norm(x, p[pre + "sa_norm.scale"]), p, pre + "attn.", config, vis, cos, sin)
+        x = x + attention(rms_norm(x, p[pre + "sa_norm.scale"]), p, pre + "attn.", config, vis, cos, sin,
+                          drop=None if drops is None else drops[i])
         x = x + swiglu(rms_norm(x, p[pre + "mlp_norm.scale"]), p, pre + "mlp.")
         if taps is not None:
             taps[f"layer{i}"] = x
@@ -226,7 +241,7 @@ def cloze_losses(hidden, d, p, config, evaluate=False):
     return out
 
 
-def step(d, p, config, randval, evaluate=False, taps=None):
+def step(d, p, config, randval, evaluate=False, taps=None, drops=None):
     """transformer.model.py:493-529 train_forward.  d: dict of flat or [B,S]
     tensors; returns (losses, masked batch)."""
     S = config["max_sequence_length"]
@@ -236,7 +251,7 @@ def step(d, p, config, randval, evaluate=False, taps=None):
     vis = visibility(dm["userid"], dm["token_mask_ids"])
     if taps is not None:
         taps["x0"] = x0
-    hidden = trunk(x0, p, config, vis, taps=taps)
+    hidden = trunk(x0, p, config, vis, taps=taps, drops=drops)
     if taps is not None:
         taps["hidden"] = hidden
     return cloze_losses(hidden, dm, p, config, evaluate), dm
@@ -259,28 +274,33 @@ def inference_forward(d, p, config, task):
     return F.linear(h, p["rating_head.2.weight"], p["rating_head.2.bias"])
 
 
-def step_with_grads(d, p, config, randval, task_weights, autocast=False):
+def step_with_grads(d, p, config, randval, task_weights, autocast=False, drops=None):
     """Forward + backward as transformer.py:256-272 drives it; returns
     (losses, grads dict keyed like p for float leaves that require grad)."""
     leaves = {}
     for k, v in p.items():
         t = v.detach().clone()
-        if t.is_floating_point() and k != "item_embedding.metadata_embedding.embedding.weight":
+        trainable = t.is_floating_point() and k != "item_embedding.metadata_embedding.embedding.weight"
+        if config.get("finetune"):  # transformer.model.py:361-371: only the LoRA matrices train
+            trainable = "lora_" in k
+        if trainable:
             t.requires_grad_(True)
         leaves[k] = t
     dev = "cuda" if next(iter(leaves.values())).is_cuda else "cpu"
     with torch.autocast(dev, dtype=torch.bfloat16, enabled=autocast):
-        losses, dm = step(d, leaves, config, randval)
+        losses, dm = step(d, leaves, config, randval, drops=drops)
         total = sum(l * w for l, w in zip(losses, task_weights))
     total.backward()
     grads = {k: v.grad for k, v in leaves.items() if v.requires_grad and v.grad is not None}
     return [l.detach() for l in losses], grads, dm
 
 
-def default_task_weights():
-    """transformer.py:379-406 with no finetune flags."""
+def default_task_weights(finetune_medium=None, finetune_metric=None):
+    """transformer.py:379-406 `make_task_weights`: order [0.watch, 0.rating, 1.watch, 1.rating]."""
     scale = [4.618602403897067, 1.1958987168236102, 2.5443243303769867, 1.0527565486045412]
-    w = [0.25 * 1, 0.25 * 0.25, 1 * 1, 1 * 0.25]
+    metric_w = {"watch": 1, "rating": 0.25} if finetune_metric is None else {m: float(m == finetune_metric) for m in METRICS}
+    medium_w = {0: 0.25, 1: 1} if finetune_medium is None else {finetune_medium: 1, 1 - finetune_medium: 0}
+    w = [medium_w[m] * metric_w[k] for m in MEDIUMS for k in METRICS]
     tot = sum(w)
     return [(x / tot) / s for x, s in zip(w, scale)]
 

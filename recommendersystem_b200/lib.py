@@ -59,7 +59,7 @@ class AttnArgs(C.Structure):
 
 
 (EPI_BF16, EPI_F32, EPI_F32_ACCUM, EPI_RESID, EPI_BIAS_BF16, EPI_BIAS_GELU, EPI_CE_PARTIAL, EPI_CE_GRAD, EPI_TABLE,
- EPI_SWIGLU, EPI_ROPE) = range(11)
+ EPI_SWIGLU, EPI_ROPE, EPI_BF16_ACCUM) = range(12)
 
 _lib = None
 
@@ -71,7 +71,7 @@ GEMM_EVENTS = None
 _LAUNCHES_PER_CALL = {
     "graft_jagged_offsets": 2, "graft_action_embed": 2, "graft_action_embed_bwd": 5, "graft_scatter_add_sorted": 6,
     "graft_rmsnorm_bwd": 2, "graft_colsum": 2, "graft_attn_bwd": 3, "graft_ce_finish": 2, "graft_rating_tail": 2,
-    "graft_rating_tail_bwd": 2, "graft_sumsq_f32": 2, "graft_jagged_offsets_host": 0, "graft_block_permutation_host": 0,
+    "graft_rating_tail_bwd": 3, "graft_sumsq_f32": 2, "graft_jagged_offsets_host": 0, "graft_block_permutation_host": 0,
     "graft_concat_pad_host": 0,
 }
 
@@ -253,10 +253,11 @@ def ce_nblocks(N):
 
 
 # ------------------------------------------------------------- element-wise --
-def rmsnorm_fwd(x, scale, y16, y32, rstd, eps=1e-5):
+def rmsnorm_fwd(x, scale, y16, y32, rstd, eps=1e-5, delta=None, h_out=None):
+    """y = norm(x) or, with `delta` (bf16), h_out = x + delta and y = norm(h_out)."""
     T, d = x.shape
-    _check(load().graft_rmsnorm_fwd(ptr(x), ptr(scale), ptr(y16), ptr(y32), ptr(rstd), i64(T), d, f32(eps), stream()),
-           "graft_rmsnorm_fwd")
+    _check(load().graft_rmsnorm_fwd(ptr(x), ptr(delta), ptr(h_out), ptr(scale), ptr(y16), ptr(y32), ptr(rstd), i64(T), d, f32(eps),
+                                    stream()), "graft_rmsnorm_fwd")
 
 
 def rmsnorm_bwd(x, scale, rstd, dy16, dy32, dres, dx, dx16, dscale):
@@ -298,6 +299,14 @@ def colsum(src, out):
     f, b = (ptr(src), None) if src.dtype == torch.float32 else (None, ptr(src))
     _check(load().graft_colsum(f, b, i64(rows), i64(cols), i64(cols), ptr(out), ptr(ws), i64(ws.numel()), stream()),
            "graft_colsum")
+
+
+def mul_to_bf16(a, mask, out):
+    _check(load().graft_mul_to_bf16(ptr(a), ptr(mask), ptr(out), i64(a.numel()), stream()), "graft_mul_to_bf16")
+
+
+def fma_mask_bf16(y, t, mask):
+    _check(load().graft_fma_mask_bf16(ptr(y), ptr(t), ptr(mask), i64(y.numel()), stream()), "graft_fma_mask_bf16")
 
 
 def axpy(y, x, alpha):

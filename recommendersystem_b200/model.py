@@ -62,15 +62,43 @@ class ActionEmbedding(nn.Module):
 
 
 class ItemEmbedding(nn.Module):
+    """ref:96-145.  Un-fused: id table + frozen metadata table + projection.  Fused
+    (finetune inference from construction; finetune training after the checkpoint is loaded,
+    ref:116-133): one [V+1, d] buffer `fused_embedding`, computed in fp32 exactly as
+    ItemEmbedding.fuse() does - a load-time step, not part of the training step."""
+
     def __init__(self, config):
         super().__init__()
         vocab = sum(config["vocab_sizes"][f"{m}_matchedid"] for m in ALL_MEDIUMS)
         self.vocab_size = vocab
+        self.fused = bool(config["finetune"]) and config["forward"] == "inference"
+        if self.fused:
+            self.register_buffer("fused_embedding", torch.empty(vocab + 1, config["embed_dim"]))
+            return
         self.matchedid_embedding = MaskedEmbedding(vocab, config["embed_dim"])
         self.metadata_embedding = MaskedEmbedding(vocab, config["metadata_emb_size"])
         for p in self.metadata_embedding.parameters():
             p.requires_grad = False  # ref:113-114
         self.projection_layer = nn.Linear(config["metadata_emb_size"], config["embed_dim"])
+        self.register_load_state_dict_pre_hook(self.reject_fused_checkpoint)
+        if config["finetune"]:
+            self.register_load_state_dict_post_hook(lambda module, _: module.fuse())
+
+    def fuse(self):
+        if self.fused:
+            return
+        with torch.no_grad():
+            fused = self.matchedid_embedding.embedding.weight + torch.nn.functional.linear(
+                self.metadata_embedding.embedding.weight, self.projection_layer.weight, self.projection_layer.bias)
+        self.register_buffer("fused_embedding", fused)
+        del self.matchedid_embedding
+        del self.metadata_embedding
+        del self.projection_layer
+        self.fused = True
+
+    @staticmethod
+    def reject_fused_checkpoint(module, state_dict, prefix, *args):
+        assert (prefix + "fused_embedding") not in state_dict
 
 
 class DualItemEmbedding(nn.Module):
@@ -106,6 +134,13 @@ class FlashAttention(nn.Module):  # name kept for state_dict/module-tree parity 
         self.k_proj = nn.Linear(d, G * hd, bias=False)
         self.v_proj = nn.Linear(d, G * hd, bias=False)
         self.output_proj = nn.Linear(H * hd, d, bias=False)
+        if config["finetune"]:  # LoRA r=8, alpha=16 on q and v, ref:235-254
+            self.q_proj_lora_A = nn.Linear(d, 8, bias=False)
+            self.q_proj_lora_B = nn.Linear(8, H * hd, bias=False)
+            self.v_proj_lora_A = nn.Linear(d, 8, bias=False)
+            self.v_proj_lora_B = nn.Linear(8, G * hd, bias=False)
+            # (the reference zeroes *_lora_B here, ref:252-254, but RecommenderModel's
+            # self.apply(init_weights), ref:360, re-draws every Linear afterwards: B is N(0, .006))
 
 
 class TransformerBlock(nn.Module):
@@ -147,9 +182,15 @@ class _Params:
         add("ae.gender", ae.gender_embedding.embedding.weight)
         add("ae.source", ae.source_embedding.embedding.weight)
         add("ae.w", ae.linear.weight); add("ae.b", ae.linear.bias)
-        add("ie.id", ie.matchedid_embedding.embedding.weight)
-        add("ie.pw", ie.projection_layer.weight); add("ie.pb", ie.projection_layer.bias)
+        self.fused = ie.fused
+        self.lora = bool(model.config["finetune"])
+        if not ie.fused:
+            add("ie.id", ie.matchedid_embedding.embedding.weight)
+            add("ie.pw", ie.projection_layer.weight); add("ie.pb", ie.projection_layer.bias)
         for i, l in enumerate(tr.layers):
+            if self.lora:
+                add(f"l{i}.qA", l.attn.q_proj_lora_A.weight); add(f"l{i}.qB", l.attn.q_proj_lora_B.weight)
+                add(f"l{i}.vA", l.attn.v_proj_lora_A.weight); add(f"l{i}.vB", l.attn.v_proj_lora_B.weight)
             add(f"l{i}.q", l.attn.q_proj.weight); add(f"l{i}.k", l.attn.k_proj.weight)
             add(f"l{i}.v", l.attn.v_proj.weight); add(f"l{i}.o", l.attn.output_proj.weight)
             add(f"l{i}.w1", l.mlp.w1.weight); add(f"l{i}.w2", l.mlp.w2.weight); add(f"l{i}.w3", l.mlp.w3.weight)
@@ -178,7 +219,7 @@ class _ClozeStep(torch.autograd.Function):
         cfg = model.config
         P = model._params
         W = dict(zip(P.names, params))
-        dev = W["ie.id"].device
+        dev = W["ae.w"].device
         if dev.type != "cuda":
             raise L.GraftError("the cloze step has no CPU path: move the model and batch to a CUDA device")
         B, S = d["userid"].shape
@@ -207,14 +248,28 @@ class _ClozeStep(torch.autograd.Function):
             w2 = _bf16((dm, I), dev); L.cast_bf16(W[f"l{i}.w2"], w2)
             wq.append((qkv_w, o_w, w13, w2))
         sv["wq"] = wq
+        lw = []
+        if P.lora:
+            for i in range(nl):
+                Aq = torch.zeros((64, dm), dtype=torch.bfloat16, device=dev); Aq[:8].copy_(W[f"l{i}.qA"])
+                Av = torch.zeros((64, dm), dtype=torch.bfloat16, device=dev); Av[:8].copy_(W[f"l{i}.vA"])
+                Bq2 = torch.zeros((H * 64, 64), dtype=torch.bfloat16, device=dev); Bq2[:, :8].copy_(2.0 * W[f"l{i}.qB"])
+                Bv2 = torch.zeros((G * 64, 64), dtype=torch.bfloat16, device=dev); Bv2[:, :8].copy_(2.0 * W[f"l{i}.vB"])
+                lw.append((Aq, Bq2, Av, Bv2))
+        sv["lw"] = lw
 
         # ---- fused item table = id rows + bf16(meta . Wp^T + bp)   (ref:120-128 / 165-169) ----
-        meta16, Mp = model._meta_bf16()
-        pw16 = _bf16((dm, Mp), dev); L.cast_pad_rows(W["ie.pw"], pw16)
-        table = _f32((Vt + 1, dm), dev)
-        L.gemm(meta16, pw16, table, Vt + 1, dm, Mp, epilogue=L.EPI_TABLE, resid=W["ie.id"], bias=W["ie.pb"])
-        table16 = _bf16((Vt + 1, dm), dev); L.cast_bf16(table, table16)
-        sv["pw16"], sv["table16"] = pw16, table16
+        if P.fused:  # finetune: frozen, fused once at load time (ref:116-133)
+            table, table16 = model._fused_tables()
+            Mp = 0
+        else:
+            meta16, Mp = model._meta_bf16()
+            pw16 = _bf16((dm, Mp), dev); L.cast_pad_rows(W["ie.pw"], pw16)
+            table = _f32((Vt + 1, dm), dev)
+            L.gemm(meta16, pw16, table, Vt + 1, dm, Mp, epilogue=L.EPI_TABLE, resid=W["ie.id"], bias=W["ie.pb"])
+            table16 = _bf16((Vt + 1, dm), dev); L.cast_bf16(table, table16)
+            sv["pw16"] = pw16
+        sv["table16"] = table16
 
         # ---- tokens: x0[2i] = table[id], x0[2i+1] = action Linear (ref:464-467) ----
         x = _f32((T, dm), dev)
@@ -233,27 +288,60 @@ class _ClozeStep(torch.autograd.Function):
 
         # ---- block stack (ref:297-343) ----
         layers = []
+        dlt = None  # bf16 output of the previous block's w2 GEMM: its residual add rides on the next norm
         for i in range(nl):
             qkv_w, o_w, w13, w2 = wq[i]
             xn = _bf16((T, dm), dev); r1 = _f32((T,), dev)
-            L.rmsnorm_fwd(x, W[f"l{i}.san"], xn, None, r1)
+            if dlt is None:
+                L.rmsnorm_fwd(x, W[f"l{i}.san"], xn, None, r1)
+            else:  # x = h_prev + mlp(h_prev), ref:307-308
+                xs = _f32((T, dm), dev)
+                L.rmsnorm_fwd(x, W[f"l{i}.san"], xn, None, r1, delta=dlt, h_out=xs)
+                x = xs
             qkv = _bf16((T, QKV), dev)
-            L.gemm(xn, qkv_w, qkv, T, QKV, dm, epilogue=L.EPI_ROPE, rope=dict(cos=cos, sin=sin, cols=(H + G) * 64, row_len=2 * S))
+            lora = None
+            if not P.lora:
+                L.gemm(xn, qkv_w, qkv, T, QKV, dm, epilogue=L.EPI_ROPE, rope=dict(cos=cos, sin=sin, cols=(H + G) * 64, row_len=2 * S))
+            else:
+                # LoRA on q and v (ref:263-271): q += 2 * B_q (A_q drop(x)), v likewise; rank padded 8 -> 64 with
+                # zeros so the two skinny GEMMs use the regular tiles; the factor 2 = alpha/r is folded into B
+                L.gemm(xn, qkv_w, qkv, T, QKV, dm)
+                xq = xv = xn
+                mq = mv = None
+                if model.training:  # nn.Dropout(0.1) on the LoRA input, independent masks for q and v
+                    xn32 = _f32((T, dm), dev)
+                    L.rmsnorm_fwd(x, W[f"l{i}.san"], None, xn32, None)
+                    mq, mv = model._lora_dropout(i, "q", (B, 2 * S, dm), dev), model._lora_dropout(i, "v", (B, 2 * S, dm), dev)
+                    xq = _bf16((T, dm), dev); L.mul_to_bf16(xn32, mq, xq)
+                    xv = _bf16((T, dm), dev); L.mul_to_bf16(xn32, mv, xv)
+                    del xn32
+                Aq, Bq2, Av, Bv2 = lw[i]
+                aq = _bf16((T, 64), dev); L.gemm(xq, Aq, aq, T, 64, dm)
+                L.gemm(aq, Bq2, qkv, T, H * 64, 64, ldc=QKV, epilogue=L.EPI_BF16_ACCUM)
+                av = _bf16((T, 64), dev); L.gemm(xv, Av, av, T, 64, dm)
+                L.gemm(av, Bv2, qkv[:, (H + G) * 64:], T, G * 64, 64, ldc=QKV, epilogue=L.EPI_BF16_ACCUM)
+                L.rope(qkv, H + G, 2 * S, cos, sin)
+                lora = (aq, av, xq, xv, mq, mv)
             ao = _bf16((T, H * 64), dev); lse = _f32((H, T), dev)
             at = L.attn_args(qkv, H, G, B, 2 * S, tm_tok, seg_s, seg_e)
             L.attn_fwd(at, ao, lse)
-            h = _f32((T, dm), dev)
-            L.gemm(ao, o_w, h, T, dm, H * 64, epilogue=L.EPI_RESID, resid=x)
-            hn = _bf16((T, dm), dev); r2 = _f32((T,), dev)
-            L.rmsnorm_fwd(h, W[f"l{i}.mln"], hn, None, r2)
+            dl1 = _bf16((T, dm), dev)
+            L.gemm(ao, o_w, dl1, T, dm, H * 64)
+            h = _f32((T, dm), dev); hn = _bf16((T, dm), dev); r2 = _f32((T,), dev)
+            L.rmsnorm_fwd(x, W[f"l{i}.mln"], hn, None, r2, delta=dl1, h_out=h)  # h = x + attn(...), ref:304-306
             gu = _bf16((T, 2 * I), dev); act = _bf16((T, I), dev)
             L.gemm(hn, w13, gu, T, 2 * I, dm, epilogue=L.EPI_SWIGLU, aux=act, ldaux=I)
-            xo = _f32((T, dm), dev)
-            L.gemm(act, w2, xo, T, dm, I, epilogue=L.EPI_RESID, resid=h)
-            layers.append((x, xn, r1, qkv, ao, lse, h, hn, r2, gu, act))
-            x = xo
+            dlt = dl1  # reuse the buffer for the mlp output
+            L.gemm(act, w2, dlt, T, dm, I)
+            layers.append((x, xn, r1, qkv, ao, lse, h, hn, r2, gu, act, lora))
+            x = h
         hidden = _f32((T, dm), dev); rF = _f32((T,), dev)
-        L.rmsnorm_fwd(x, W["norm"], None, hidden, rF)
+        if dlt is None:
+            L.rmsnorm_fwd(x, W["norm"], None, hidden, rF)
+        else:
+            xs = _f32((T, dm), dev)
+            L.rmsnorm_fwd(x, W["norm"], None, hidden, rF, delta=dlt, h_out=xs)
+            x = xs
         sv["layers"], sv["xL"], sv["rF"] = layers, x, rF
         if model._taps is not None:
             model._taps.update(x0=layers[0][0] if nl else x, hidden=hidden,
@@ -337,9 +425,14 @@ class _ClozeStep(torch.autograd.Function):
         dev = gout.device
         gout = gout.contiguous().float()
         G_ = {}  # name -> grad tensor
+        need = dict(zip(P.names, ctx.needs_input_grad[3:]))  # finetune: only the LoRA matrices (ref:361-371)
+        base = not P.lora          # the block / head / embedding weights train
+        tab = not P.fused          # the item table trains (pre-train mode)
 
-        dtable = _f32((Vt + 1, dm), dev)
-        dtable[Vt].zero_()  # rows [0,Vt) are fully written by the head GEMMs below
+        dtable = None
+        if tab:
+            dtable = _f32((Vt + 1, dm), dev)
+            dtable[Vt].zero_()  # rows [0,Vt) are fully written by the head GEMMs below
         dhid = torch.zeros((T, dm), dtype=torch.float32, device=dev)
         table16 = sv["table16"]
         CH = 4096
@@ -359,7 +452,8 @@ class _ClozeStep(torch.autograd.Function):
                 rows_n, hs_rows, tgt_rows = vp["hs_all"].shape[0], vp["hs_all"], vp["pos_loc"]
                 lse_rows, coef_rows = comm.all_gather_rows(hd["lse"]), comm.all_gather_rows(coef)
                 c_lo, c_hi, lim = vp["s0"], vp["s1"], None
-                dtable[lo:c_lo].zero_(); dtable[c_hi:hi].zero_()  # other slices: their owners write them
+                if tab:
+                    dtable[lo:c_lo].zero_(); dtable[c_hi:hi].zero_()  # other slices: their owners write them
             dhs = _f32((rows_n, dm), dev)
             dlog = _bf16((rows_n, CH), dev)
             for c0 in range(0, c_hi - c_lo, CH):
@@ -371,20 +465,22 @@ class _ClozeStep(torch.autograd.Function):
                 L.gemm(dlog, items, dhs, rows_n, dm, cn, lda=CH, b_kmajor=False, ldb=dm,
                        epilogue=L.EPI_F32 if c0 == 0 else L.EPI_F32_ACCUM, m_count=lim)
                 # d table rows = dlogits^T . hidden rows
-                L.gemm(dlog, hs_rows, dtable[c_lo + c0: c_lo + c0 + cn], cn, dm, rows_n, a_kmajor=False, lda=CH, b_kmajor=False,
-                       ldb=dm, epilogue=L.EPI_F32, split_k=-1, k_count=lim)
+                if tab:
+                    L.gemm(dlog, hs_rows, dtable[c_lo + c0: c_lo + c0 + cn], cn, dm, rows_n, a_kmajor=False, lda=CH,
+                           b_kmajor=False, ldb=dm, epilogue=L.EPI_F32, split_k=-1, k_count=lim)
             if hd["vp"] is not None:
                 dhs = comm.reduce_scatter_rows(dhs)  # sum of the shards' partial d(hidden rows), my rows only
             L.scatter_rows_f32(dhs, hd["sel"], 0, dhid)
             # ---- rating head backward ----
-            dpre = _bf16((cap, dm), dev); dp = _f32((cap,), dev)
+            dpre = _bf16((cap, dm), dev); dp = _f32((cap + 32 * (dm + 1),), dev)
             loss4 = sv["out"][4 + 4 * m: 8 + 4 * m]
             L.rating_tail_bwd(hd["pre"], hd["h1"], W["rh.w2"], hd["rlab"], hd["rws"], cfg["rating_mean"], hd["pred"], loss4,
                               gout[2 * m + 1], dpre, dp, tmp_dw2, tmp_db2)
-            dw2 += tmp_dw2; db2 += tmp_db2
-            L.gemm(dpre, hd["rhs"], dw0, dm, dm, cap, a_kmajor=False, lda=dm, b_kmajor=False, ldb=dm,
-                   epilogue=L.EPI_F32 if m == 0 else L.EPI_F32_ACCUM, split_k=-1)
-            L.colsum(dpre, tmp_db0); db0 += tmp_db0
+            if base:
+                dw2 += tmp_dw2; db2 += tmp_db2
+                L.gemm(dpre, hd["rhs"], dw0, dm, dm, cap, a_kmajor=False, lda=dm, b_kmajor=False, ldb=dm,
+                       epilogue=L.EPI_F32 if m == 0 else L.EPI_F32_ACCUM, split_k=-1)
+                L.colsum(dpre, tmp_db0); db0 += tmp_db0
             drhs = _f32((cap, dm), dev)
             L.gemm(dpre, sv["w0_16"], drhs, cap, dm, dm, b_kmajor=False, ldb=dm, epilogue=L.EPI_F32)
             L.scatter_rows_f32(drhs, hd["rsel"], 1, dhid)
@@ -400,43 +496,80 @@ class _ClozeStep(torch.autograd.Function):
         cos, sin = model.transformers.freqs_cos, model.transformers.freqs_sin
 
         for i in reversed(range(nl)):
-            x, xn, r1, qkv, ao, lse, h, hn, r2, gu, act = sv["layers"][i]
+            x, xn, r1, qkv, ao, lse, h, hn, r2, gu, act, lora = sv["layers"][i]
             qkv_w, o_w, w13, w2 = sv["wq"][i]
             # x_out = h + act . W2^T
             dact = _bf16((T, I), dev)
             L.gemm(dx16, w2, dact, T, I, dm, b_kmajor=False, ldb=I)
-            g_w2 = _f32((dm, I), dev)
-            L.gemm(dx16, act, g_w2, dm, I, T, a_kmajor=False, lda=dm, b_kmajor=False, ldb=I, epilogue=L.EPI_F32, split_k=-1)
+            if base:
+                g_w2 = _f32((dm, I), dev)
+                L.gemm(dx16, act, g_w2, dm, I, T, a_kmajor=False, lda=dm, b_kmajor=False, ldb=I, epilogue=L.EPI_F32, split_k=-1)
             dgu = _bf16((T, 2 * I), dev)
             L.swiglu_bwd(gu, dact, dgu, interleaved64=True)
             del dact
             dhn = _bf16((T, dm), dev)
             L.gemm(dgu, w13, dhn, T, dm, 2 * I, b_kmajor=False, ldb=dm)
-            g_w13 = _f32((2 * I, dm), dev)
-            L.gemm(dgu, hn, g_w13, 2 * I, dm, T, a_kmajor=False, lda=2 * I, b_kmajor=False, ldb=dm, epilogue=L.EPI_F32, split_k=-1)
+            if base:
+                g_w13 = _f32((2 * I, dm), dev)
+                L.gemm(dgu, hn, g_w13, 2 * I, dm, T, a_kmajor=False, lda=2 * I, b_kmajor=False, ldb=dm, epilogue=L.EPI_F32,
+                       split_k=-1)
             del dgu
             dh = _f32((T, dm), dev); dh16 = _bf16((T, dm), dev); g_mln = _f32((dm,), dev)
             L.rmsnorm_bwd(h, W[f"l{i}.mln"], r2, dhn, None, dx, dh, dh16, g_mln)
             # h = x + ao . Wo^T
             dao = _bf16((T, H * 64), dev)
             L.gemm(dh16, o_w, dao, T, H * 64, dm, b_kmajor=False, ldb=H * 64)
-            g_o = _f32((dm, H * 64), dev)
-            L.gemm(dh16, ao, g_o, dm, H * 64, T, a_kmajor=False, lda=dm, b_kmajor=False, ldb=H * 64, epilogue=L.EPI_F32, split_k=-1)
+            if base:
+                g_o = _f32((dm, H * 64), dev)
+                L.gemm(dh16, ao, g_o, dm, H * 64, T, a_kmajor=False, lda=dm, b_kmajor=False, ldb=H * 64, epilogue=L.EPI_F32,
+                       split_k=-1)
             dqkv = _bf16((T, QKV), dev); delta = _f32((H, T), dev)
             at = L.attn_args(qkv, H, G, B, 2 * S, tm_tok, seg_s, seg_e)
             L.attn_bwd(at, ao, dao, lse, dqkv, delta)
             L.rope(dqkv, H + G, 2 * S, cos, sin, inverse=True)
             dxn = dhn  # reuse
+            if lora is not None:
+                # q = q0 + (A_q xq) B2_q^T with B2 = 2B:  d(A x) = dq . B2,  dB = 2 dq^T (A x),  dA = d(Ax)^T xq
+                aq, av, xq, xv, mq, mv = lora
+                Aq, Bq2, Av, Bv2 = sv["lw"][i]
+                d_aq = _bf16((T, 64), dev); d_av = _bf16((T, 64), dev)
+                dv_view = dqkv[:, (H + G) * 64:]
+                L.gemm(dqkv, Bq2, d_aq, T, 64, H * 64, lda=QKV, b_kmajor=False, ldb=64)
+                L.gemm(dv_view, Bv2, d_av, T, 64, G * 64, lda=QKV, b_kmajor=False, ldb=64)
+                gBq = _f32((H * 64, 64), dev); gBv = _f32((G * 64, 64), dev); gAq = _f32((64, dm), dev); gAv = _f32((64, dm), dev)
+                L.gemm(dqkv, aq, gBq, H * 64, 64, T, a_kmajor=False, lda=QKV, b_kmajor=False, ldb=64, epilogue=L.EPI_F32, split_k=-1)
+                L.gemm(dv_view, av, gBv, G * 64, 64, T, a_kmajor=False, lda=QKV, b_kmajor=False, ldb=64, epilogue=L.EPI_F32, split_k=-1)
+                L.gemm(d_aq, xq, gAq, 64, dm, T, a_kmajor=False, lda=64, b_kmajor=False, ldb=dm, epilogue=L.EPI_F32, split_k=-1)
+                L.gemm(d_av, xv, gAv, 64, dm, T, a_kmajor=False, lda=64, b_kmajor=False, ldb=dm, epilogue=L.EPI_F32, split_k=-1)
+                G_[f"l{i}.qB"], G_[f"l{i}.vB"] = 2.0 * gBq[:, :8], 2.0 * gBv[:, :8]
+                G_[f"l{i}.qA"], G_[f"l{i}.vA"] = gAq[:8], gAv[:8]
+                if i == 0 and not tab:
+                    sv["layers"][i] = None
+                    break  # nothing below the first block trains (ref:361-371)
             L.gemm(dqkv, qkv_w, dxn, T, dm, QKV, b_kmajor=False, ldb=dm)
-            g_qkv = _f32((QKV, dm), dev)
-            L.gemm(dqkv, xn, g_qkv, QKV, dm, T, a_kmajor=False, lda=QKV, b_kmajor=False, ldb=dm, epilogue=L.EPI_F32, split_k=-1)
+            if lora is not None:  # d(norm output) also flows through the LoRA branches (and their dropout masks)
+                if mq is None:
+                    L.gemm(d_aq, Aq, dxn, T, dm, 64, b_kmajor=False, ldb=dm, epilogue=L.EPI_BF16_ACCUM)
+                    L.gemm(d_av, Av, dxn, T, dm, 64, b_kmajor=False, ldb=dm, epilogue=L.EPI_BF16_ACCUM)
+                else:
+                    tmp = _bf16((T, dm), dev)
+                    L.gemm(d_aq, Aq, tmp, T, dm, 64, b_kmajor=False, ldb=dm); L.fma_mask_bf16(dxn, tmp, mq)
+                    L.gemm(d_av, Av, tmp, T, dm, 64, b_kmajor=False, ldb=dm); L.fma_mask_bf16(dxn, tmp, mv)
+            if base:
+                g_qkv = _f32((QKV, dm), dev)
+                L.gemm(dqkv, xn, g_qkv, QKV, dm, T, a_kmajor=False, lda=QKV, b_kmajor=False, ldb=dm, epilogue=L.EPI_F32, split_k=-1)
             g_san = _f32((dm,), dev)
             L.rmsnorm_bwd(x, W[f"l{i}.san"], r1, dxn, None, dh, dx, dx16, g_san)
-            G_[f"l{i}.q"], G_[f"l{i}.k"], G_[f"l{i}.v"] = g_qkv[: H * 64], g_qkv[H * 64:(H + G) * 64], g_qkv[(H + G) * 64:]
-            g13 = g_w13.view(I // 64, 2, 64, dm)  # rows are in the interleaved gate/up block order
-            G_[f"l{i}.o"], G_[f"l{i}.w1"], G_[f"l{i}.w3"], G_[f"l{i}.w2"] = g_o, g13[:, 0].reshape(I, dm), g13[:, 1].reshape(I, dm), g_w2
-            G_[f"l{i}.san"], G_[f"l{i}.mln"] = g_san, g_mln
+            if base:
+                G_[f"l{i}.q"], G_[f"l{i}.k"], G_[f"l{i}.v"] = g_qkv[: H * 64], g_qkv[H * 64:(H + G) * 64], g_qkv[(H + G) * 64:]
+                g13 = g_w13.view(I // 64, 2, 64, dm)  # rows are in the interleaved gate/up block order
+                G_[f"l{i}.o"], G_[f"l{i}.w1"], G_[f"l{i}.w3"], G_[f"l{i}.w2"] = g_o, g13[:, 0].reshape(I, dm), g13[:, 1].reshape(I, dm), g_w2
+                G_[f"l{i}.san"], G_[f"l{i}.mln"] = g_san, g_mln
             sv["layers"][i] = None  # free this layer's activations
+
+        if not base:  # finetune: embeddings, heads and block weights are frozen
+            ctx.sv = None
+            return (None, None, None, *[(G_[n].contiguous() if nd else None) for n, nd in need.items()])
 
         # ---- token embeddings ----
         L.scatter_add_sorted(dx, 2 * dm, sv["mid"], dm, dtable)  # item rows of the interleaved stream
@@ -469,7 +602,7 @@ def _inference_hidden(model, d):
     final-norm output [U, 2S', d] fp32.  Same kernels as the train forward; nothing is kept."""
     cfg, P = model.config, model._params
     W = dict(zip(P.names, P.tensors))
-    dev = W["ie.id"].device
+    dev = W["ae.w"].device
     if dev.type != "cuda":
         raise L.GraftError("the inference forward has no CPU path: move the model and batch to a CUDA device")
     B, S = d["userid"].shape
@@ -495,18 +628,27 @@ def _inference_hidden(model, d):
         assert 2 * S <= cos.shape[0], "row longer than the RoPE table (2 * max_sequence_length)"
     xn = _bf16((T, dm), dev); qkv = _bf16((T, QKV), dev); ao = _bf16((T, H * 64), dev); lse = _f32((H, T), dev)
     gu = _bf16((T, 2 * I), dev); act = _bf16((T, I), dev)
+    dl = _bf16((T, dm), dev)
+    h = _f32((T, dm), dev)
+    first = True
     for i in range(cfg["num_layers"]):
         qkv_w, o_w, w13, w2 = wts["layers"][i]
-        L.rmsnorm_fwd(x, W[f"l{i}.san"], xn, None, None)
+        if first:
+            L.rmsnorm_fwd(x, W[f"l{i}.san"], xn, None, None)
+        else:
+            L.rmsnorm_fwd(h, W[f"l{i}.san"], xn, None, None, delta=dl, h_out=x)  # x = h + mlp(h)
+        first = False
         L.gemm(xn, qkv_w, qkv, T, QKV, dm, epilogue=L.EPI_ROPE, rope=rope)
         L.attn_fwd(L.attn_args(qkv, H, G, B, 2 * S, tm_tok, seg_s, seg_e), ao, lse)
-        h = _f32((T, dm), dev)
-        L.gemm(ao, o_w, h, T, dm, H * 64, epilogue=L.EPI_RESID, resid=x)
-        L.rmsnorm_fwd(h, W[f"l{i}.mln"], xn, None, None)
+        L.gemm(ao, o_w, dl, T, dm, H * 64)
+        L.rmsnorm_fwd(x, W[f"l{i}.mln"], xn, None, None, delta=dl, h_out=h)      # h = x + attn(x)
         L.gemm(xn, w13, gu, T, 2 * I, dm, epilogue=L.EPI_SWIGLU, aux=act, ldaux=I)
-        L.gemm(act, w2, x, T, dm, I, epilogue=L.EPI_RESID, resid=h)
+        L.gemm(act, w2, dl, T, dm, I)
     hidden = _f32((T, dm), dev)
-    L.rmsnorm_fwd(x, W["norm"], None, hidden, None)
+    if first:
+        L.rmsnorm_fwd(x, W["norm"], None, hidden, None)
+    else:
+        L.rmsnorm_fwd(h, W["norm"], None, hidden, None, delta=dl, h_out=x)
     return hidden.view(B, 2 * S, dm)
 
 
@@ -514,8 +656,6 @@ class RecommenderModel(nn.Module):
     def __init__(self, config):
         super().__init__()
         self.config = config
-        if config.get("finetune"):
-            raise NotImplementedError("finetune/LoRA mode is not built yet (SURVEY.md 8f rank 4)")
         self.action_embedding = ActionEmbedding(config)
         self.item_embedding = ItemEmbedding(config)
         self.transformers = Transformer(config)
@@ -523,7 +663,15 @@ class RecommenderModel(nn.Module):
         self.rating_head = nn.Sequential(
             nn.Linear(config["embed_dim"], config["embed_dim"]), nn.GELU(), nn.Linear(config["embed_dim"], 1))
         self.apply(init_weights)
-        self._params = _Params(self)
+        if config["finetune"]:  # ref:361-371: everything frozen except the LoRA matrices
+            for layer in (self.action_embedding, self.item_embedding, self.watch_head, self.rating_head):
+                for p in layer.parameters():
+                    p.requires_grad = False
+            for name, p in self.transformers.named_parameters():
+                p.requires_grad = "lora_" in name
+        self._params_cache = None
+        self._fused_cache = None
+        self.lora_mask = None  # tests may inject f(layer, which, shape, device) -> dropout mask (0 or 1/0.9)
         self._meta_cache = None
         self._taps = None
         self.mask_rand = None  # tests may inject f(shape, device) -> randval
@@ -534,6 +682,14 @@ class RecommenderModel(nn.Module):
             self.forward = self.inference_forward
         else:
             raise AssertionError(config["forward"])
+
+    @property
+    def _params(self):
+        """Flat view of the step's tensors; rebuilt when ItemEmbedding.fuse() changed the tree."""
+        c = self._params_cache
+        if c is None or c.fused != self.item_embedding.fused:
+            c = self._params_cache = _Params(self)
+        return c
 
     # ref:379-389, with the matrix passed in or read from <datadir>/media_embeddings.h5
     def load_pretrained_embeddings(self, datadir=None, metadata=None):
@@ -548,6 +704,24 @@ class RecommenderModel(nn.Module):
             w.zero_()
             w[: mt.shape[0]].copy_(mt)
         self._meta_cache = None
+
+    def _fused_tables(self):
+        """finetune: the fused item table (fp32 buffer, ref:120-133) and its bf16 copy for the tied head."""
+        t = self.item_embedding.fused_embedding
+        key = (t.data_ptr(), t._version, str(t.device))
+        if self._fused_cache is None or self._fused_cache[0] != key:
+            t16 = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+            L.cast_bf16(t, t16)
+            self._fused_cache = (key, t16)
+        return t, self._fused_cache[1]
+
+    def _lora_dropout(self, layer, which, shape, dev):
+        """nn.Dropout(0.1) mask of the LoRA input (ref:247, 263-271), as a multiplier 0 or 1/0.9.  Drawn by
+        torch on a ones tensor of the reference's shape and dtype, in the reference's order (q then v,
+        block by block), so the generator is advanced exactly as the reference advances it."""
+        if self.lora_mask is not None:
+            return self.lora_mask(layer, which, shape, dev).reshape(-1).contiguous()
+        return torch.nn.functional.dropout(torch.ones(shape, dtype=torch.float32, device=dev), 0.1, True).reshape(-1)
 
     def _meta_bf16(self):
         """bf16 copy of the frozen metadata table, rows padded to a 16-byte pitch for TMA."""
@@ -569,25 +743,35 @@ class RecommenderModel(nn.Module):
             return self._infer_cache[1]
         cfg = self.config
         W = dict(zip(P.names, P.tensors))
-        dev = W["ie.id"].device
+        dev = W["ae.w"].device
         dm, H, G, I = cfg["embed_dim"], cfg["num_heads"], cfg["num_kv_heads"], cfg["intermediate_dim"]
         QKV = (H + 2 * G) * 64
         layers = []
         for i in range(cfg["num_layers"]):
             qkv_w = _bf16((QKV, dm), dev)
-            L.cast_bf16(W[f"l{i}.q"], qkv_w[: H * 64]); L.cast_bf16(W[f"l{i}.k"], qkv_w[H * 64:(H + G) * 64])
-            L.cast_bf16(W[f"l{i}.v"], qkv_w[(H + G) * 64:])
+            wq_, wv_ = W[f"l{i}.q"].detach(), W[f"l{i}.v"].detach()
+            if P.lora:
+                # inference has no dropout, so the LoRA branch (ref:263-271) is a rank-8 update of the weight:
+                # W + (alpha/r) B A, merged once in fp32 (the reference adds the two bf16 GEMM outputs instead;
+                # the difference is bf16 rounding noise, inside the 1e-2 tolerance)
+                wq_ = wq_ + 2.0 * (W[f"l{i}.qB"].detach() @ W[f"l{i}.qA"].detach())
+                wv_ = wv_ + 2.0 * (W[f"l{i}.vB"].detach() @ W[f"l{i}.vA"].detach())
+            L.cast_bf16(wq_.contiguous(), qkv_w[: H * 64]); L.cast_bf16(W[f"l{i}.k"], qkv_w[H * 64:(H + G) * 64])
+            L.cast_bf16(wv_.contiguous(), qkv_w[(H + G) * 64:])
             o_w = _bf16((dm, H * 64), dev); L.cast_bf16(W[f"l{i}.o"], o_w)
             w13 = _bf16((2 * I, dm), dev)
             w13v = w13.view(I // 64, 2, 64, dm)
             w13v[:, 0].copy_(W[f"l{i}.w1"].detach().view(I // 64, 64, dm)); w13v[:, 1].copy_(W[f"l{i}.w3"].detach().view(I // 64, 64, dm))
             w2 = _bf16((dm, I), dev); L.cast_bf16(W[f"l{i}.w2"], w2)
             layers.append((qkv_w, o_w, w13, w2))
-        meta16, Mp = self._meta_bf16()
-        pw16 = _bf16((dm, Mp), dev); L.cast_pad_rows(W["ie.pw"].detach(), pw16)
-        Vt1 = W["ie.id"].shape[0]
-        table = _f32((Vt1, dm), dev)
-        L.gemm(meta16, pw16, table, Vt1, dm, Mp, epilogue=L.EPI_TABLE, resid=W["ie.id"].detach(), bias=W["ie.pb"].detach())
+        if P.fused:
+            table = self.item_embedding.fused_embedding
+        else:
+            meta16, Mp = self._meta_bf16()
+            pw16 = _bf16((dm, Mp), dev); L.cast_pad_rows(W["ie.pw"].detach(), pw16)
+            Vt1 = W["ie.id"].shape[0]
+            table = _f32((Vt1, dm), dev)
+            L.gemm(meta16, pw16, table, Vt1, dm, Mp, epilogue=L.EPI_TABLE, resid=W["ie.id"].detach(), bias=W["ie.pb"].detach())
         w0_16 = _bf16((dm, dm), dev); L.cast_bf16(W["rh.w0"], w0_16)
         out = dict(layers=layers, table=table, w0_16=w0_16)
         self._infer_cache = (key, out)
@@ -635,10 +819,20 @@ class RecommenderModel(nn.Module):
     def mask_tokens(self, d):
         """ref:417-462 (pre-train branch): same draws, same in-place edits of `d`."""
         shape, dev = d["userid"].shape, d["userid"].device
-        randval = self.mask_rand(shape, dev) if self.mask_rand is not None else torch.rand(shape, device=dev)
-        rate = self.config["mask_rate"]
-        watch = randval < rate
-        rating = (randval >= rate) & (randval < 2 * rate)
+        if self.config["finetune"]:  # ref:418-435: the held-out targets of the finetuned metric are the masked positions
+            pick = self.config["finetune_metric"]
+            assert pick in ALL_METRICS
+            hit = torch.zeros(shape, dtype=torch.bool, device=dev)
+            for k in d:
+                if pick in k and k.endswith(".weight"):
+                    hit |= d[k] > 0
+            none = torch.zeros_like(hit)
+            watch, rating = (hit, none) if pick == "watch" else (none, hit)
+        else:
+            randval = self.mask_rand(shape, dev) if self.mask_rand is not None else torch.rand(shape, device=dev)
+            rate = self.config["mask_rate"]
+            watch = randval < rate
+            rating = (randval >= rate) & (randval < 2 * rate)
         either = watch | rating
         not_watch, not_rating = ~watch, ~rating
         d["token_mask_ids"] *= rating
@@ -663,8 +857,9 @@ class RecommenderModel(nn.Module):
     @torch.compiler.disable
     def train_forward(self, d, evaluate):
         S = self.config["max_sequence_length"]
-        for k in d:
-            d[k] = d[k].reshape(-1, S)  # ref:495-496 (mutates the caller's dict, as the trainer expects)
+        if not self.config["finetune"]:
+            for k in d:
+                d[k] = d[k].reshape(-1, S)  # ref:495-496 (mutates the caller's dict, as the trainer expects)
         d = self.mask_tokens(d)
         for k in d:
             if not d[k].is_contiguous():

@@ -366,6 +366,14 @@ def test_rmsnorm_fwd_bwd(T, d):
     L.rmsnorm_bwd(x.detach(), scale.detach(), rstd, None, dy.float(), None, dx, None, ds2)
     report("rms dx f32 path", dx, x.grad, 1e-5)
     assert torch.equal(ds, ds2)
+    # fused residual add: h = x + delta (bf16), y = norm(h); h bit-exact, y identical to the unfused call
+    delta = g_randn(T, d, seed=20).bfloat16()
+    h = torch.empty(T, d, device=DEV); yb = torch.empty_like(y16); rs2 = torch.empty(T, device=DEV)
+    L.rmsnorm_fwd(x.detach(), scale.detach(), yb, None, rs2, delta=delta, h_out=h)
+    h_ref = x.detach() + delta.float()
+    assert torch.equal(h, h_ref)
+    L.rmsnorm_fwd(h_ref, scale.detach(), y16, None, rstd)
+    assert torch.equal(yb, y16) and torch.equal(rs2, rstd)
 
 
 def test_rope_matches_reference_and_inverts():
@@ -436,7 +444,7 @@ def test_rating_tail_and_adamw():
     for i in range(3):
         assert abs(float(loss4[i]) - float(ref[i])) < 2e-2 * abs(float(ref[i]))
     # AdamW against torch
-    p = g_randn(10000, seed=30); g = g_randn(10000, seed=31)
+    p = g_randn(10003, seed=30); g = g_randn(10003, seed=31)  # odd size: vector body + scalar tail
     tp = p.clone().requires_grad_(True)
     opt = torch.optim.AdamW([tp], lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1)
     m = torch.zeros_like(p); v = torch.zeros_like(p)

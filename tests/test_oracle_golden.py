@@ -86,3 +86,41 @@ def test_inference_forward_matches_reference():
             out = oc.inference_forward(d, p, cfg, task).numpy()
         ref = z[f"{task}/out_fp32"]
         assert np.abs(out - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), task
+
+
+def _finetune_golden():
+    import json
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "finetune_tiny.npz"))
+    cfg = json.loads(bytes(z["config_json"]).decode())
+    p = {k[5:]: torch.as_tensor(z[k]) for k in z.files if k.startswith("ckpt/")}
+    for k in [k for k in p if k.startswith("item_embedding.")]:
+        del p[k]                                            # fused away at load time (transformer.model.py:120-133)
+    p["item_embedding.fused_embedding"] = torch.as_tensor(z["fused_embedding"])
+    p.update({k[5:]: torch.as_tensor(z[k]) for k in z.files if k.startswith("lora/")})
+    batch = {k[6:]: torch.as_tensor(z[k]) for k in z.files if k.startswith("batch/")}
+    S, dmod, rows = cfg["max_sequence_length"], cfg["embed_dim"], int(z["rows"])
+    masks = []
+    for i in range(cfg["num_layers"]):
+        mk = [torch.as_tensor(np.unpackbits(z[f"train/keep/{i}/{w}"])[: rows * 2 * S * dmod].reshape(rows, 2 * S, dmod).astype(np.float32))
+              / 0.9 for w in "qv"]
+        masks.append(tuple(mk))
+    return z, cfg, p, batch, masks
+
+
+def test_finetune_mode_matches_reference():
+    """LoRA on q,v, fused frozen table, finetune masking, with and without the LoRA dropout masks:
+    oracle vs the reference module in finetune mode (tests/golden/finetune_tiny.npz)."""
+    z, cfg, p, batch, masks = _finetune_golden()
+    tw = [float(x) for x in z["task_weights"]]
+    for mode, drops in (("eval", None), ("train", masks)):
+        losses, grads, dm = oc.step_with_grads(batch, p, cfg, None, tw, drops=drops)
+        np.testing.assert_allclose([float(x) for x in losses], z[f"{mode}/losses"], rtol=2e-5, atol=1e-7)
+        names = [k[len(mode) + 6:] for k in z.files if k.startswith(f"{mode}/grad/")]
+        assert sorted(names) == sorted(grads) and all("lora_" in n for n in names)
+        for n in names:
+            ref = z[f"{mode}/grad/{n}"]
+            assert np.abs(grads[n].numpy() - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-12), (mode, n)
+        if mode == "eval":
+            for k in dm:
+                assert np.array_equal(dm[k].numpy().reshape(-1), z["masked/" + k].reshape(-1)), k

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+bash tools/gpu_check.sh > gpurun_out/check.txt 2>&1; grep -E "^==|FAILED|rel " gpurun_out/check.txt | head -40
+timeout 600 python -m pytest tests/test_gpu_vocab_parallel.py tests/test_gpu_inference.py -q --tb=short -p no:cacheprovider -m gpu -s > gpurun_out/vp.log 2>&1
+echo "== vocab_parallel + inference exit $? : $(tail -n 1 gpurun_out/vp.log)"; grep -E "^rank|Error|rel vs|FAILED" gpurun_out/vp.log | head -20
+timeout 900 python bench.py --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "== bench exit $?"; cat gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err
