@@ -60,6 +60,16 @@ def main(out="finetune_tiny.npz", metric="watch"):
 
     S = cfg["max_sequence_length"]
     flat = synthetic.make_batches(cfg, rows, 1, seed=8, len_median=20.0, len_clip=(3, 80))[0]
+    # finetune data holds targets only at each user's held-out last item (Finetune/transformer.jl:52-133);
+    # that also keeps every weighted row inside the reference's top-k selection (mask_topk * B rows), the
+    # condition under which losses and gradients do not depend on torch.topk's tie order
+    u = flat["userid"]
+    last = np.r_[u[1:] != u[:-1], True] & (u > 0)
+    for k in flat:
+        if k.endswith((".label", ".weight", ".position")):
+            flat[k] = np.where(last, flat[k], 0).astype(flat[k].dtype)
+    for m in (0, 1):
+        assert (flat[f"{m}.{metric}.weight"] > 0).sum() <= cfg["mask_topk"] * rows
     batch = {k: v.reshape(rows, S) for k, v in flat.items()}
     for k in batch:
         if k.endswith(".position"):

@@ -59,7 +59,7 @@ def test_finetune_step_matches_reference(mode):
     assert np.allclose(got, ref16, rtol=1e-2, atol=1e-6) and np.allclose(got, ref32, rtol=1e-2, atol=1e-6)
     for k in d:                                      # finetune masking edits the batch like the reference
         assert np.array_equal(d[k].cpu().numpy().reshape(-1), z["masked/" + k].reshape(-1)), k
-    worst = 0.0
+    worst, bad = 0.0, []
     for n, q in model.named_parameters():
         if not q.requires_grad:
             assert q.grad is None, n
@@ -69,8 +69,11 @@ def test_finetune_step_matches_reference(mode):
         rel = np.linalg.norm(g - ref) / max(np.linalg.norm(ref), 1e-20)
         gap = np.linalg.norm(z[f"{mode}/grad_bf16/{n}"] - ref) / max(np.linalg.norm(ref), 1e-20)
         worst = max(worst, rel)
-        assert rel < max(2e-2, 2 * gap), (n, rel, gap)   # bf16 tolerance; never worse than 2x the reference's own bf16 gap
+        print(f"{mode} grad rel {rel:.3e} (reference bf16 gap {gap:.3e}) |g| {np.linalg.norm(g):.3e} |ref| {np.linalg.norm(ref):.3e} {n}")
+        if not rel < max(2e-2, 2 * gap):                 # bf16 tolerance; never worse than 2x the reference's own bf16 gap
+            bad.append((n, rel, gap))
     print(mode, "worst LoRA grad rel-L2 vs fp32 reference", worst)
+    assert not bad, bad
 
 
 def test_finetuned_inference_merges_lora():

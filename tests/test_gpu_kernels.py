@@ -139,6 +139,52 @@ def test_gemm_fused_swiglu_and_rope_epilogues():
     assert torch.equal(got, ref)
 
 
+def test_gemm_lora_shapes_and_bf16_accum():
+    """The skinny GEMMs of the LoRA branch (rank padded to 64) and the read-modify-write bf16 epilogue."""
+    T, d, HD = 512, 128, 192
+    x = g_randn(T, d, seed=31).bfloat16()
+    A = torch.zeros(64, d, device=DEV, dtype=torch.bfloat16); A[:8] = g_randn(8, d, seed=32, scale=0.2).bfloat16()
+    B2 = torch.zeros(HD, 64, device=DEV, dtype=torch.bfloat16); B2[:, :8] = g_randn(HD, 8, seed=33, scale=0.2).bfloat16()
+    ax = torch.empty(T, 64, device=DEV, dtype=torch.bfloat16)
+    L.gemm(x, A, ax, T, 64, d)
+    ax_ref = (x.float() @ A.float().t()).bfloat16()
+    report("lora A x", ax, ax_ref, 3e-3)
+    assert bool((ax[:, 8:] == 0).all())
+    # q (a column slice of a wider buffer) += ax . B2^T
+    QKV = 320
+    qkv = g_randn(T, QKV, seed=34).bfloat16()
+    ref = qkv.clone()
+    ref[:, 64:64 + HD] = (qkv[:, 64:64 + HD].float() + (ax.float() @ B2.float().t()).bfloat16().float()).bfloat16()
+    L.gemm(ax, B2, qkv[:, 64:], T, HD, 64, ldc=QKV, epilogue=L.EPI_BF16_ACCUM)
+    report("bf16 accum", qkv, ref, 3e-3)
+    assert torch.equal(qkv[:, :64], ref[:, :64]) and torch.equal(qkv[:, 64 + HD:], ref[:, 64 + HD:])
+    # backward shapes: d(Ax) = dq . B2 ; gB = dq^T (Ax) ; gA = d(Ax)^T x ; dx += d(Ax) . A
+    dqkv = g_randn(T, QKV, seed=35).bfloat16()
+    dq = dqkv[:, 64:64 + HD]
+    dax = torch.empty(T, 64, device=DEV, dtype=torch.bfloat16)
+    L.gemm(dq, B2, dax, T, 64, HD, lda=QKV, b_kmajor=False, ldb=64)
+    report("d(Ax)", dax, (dq.float() @ B2.float()).bfloat16(), 3e-3)
+    gB = torch.empty(HD, 64, device=DEV)
+    L.gemm(dq, ax, gB, HD, 64, T, a_kmajor=False, lda=QKV, b_kmajor=False, ldb=64, epilogue=L.EPI_F32, split_k=-1)
+    report("gB", gB, dq.float().t() @ ax.float(), 1e-5)
+    gA = torch.empty(64, d, device=DEV)
+    L.gemm(dax, x, gA, 64, d, T, a_kmajor=False, lda=64, b_kmajor=False, ldb=d, epilogue=L.EPI_F32, split_k=-1)
+    report("gA", gA, dax.float().t() @ x.float(), 1e-5)
+    dx = g_randn(T, d, seed=36).bfloat16()
+    dx_ref = (dx.float() + (dax.float() @ A.float()).bfloat16().float()).bfloat16()
+    L.gemm(dax, A, dx, T, d, 64, b_kmajor=False, ldb=d, epilogue=L.EPI_BF16_ACCUM)
+    report("dx accum", dx, dx_ref, 3e-3)
+    # dropout helpers
+    a32 = g_randn(T, d, seed=37); mask = (torch.rand(T, d, generator=torch.Generator().manual_seed(4)) > 0.1).float().to(DEV) / 0.9
+    o = torch.empty(T, d, device=DEV, dtype=torch.bfloat16)
+    L.mul_to_bf16(a32, mask, o)
+    assert torch.equal(o, (a32 * mask).bfloat16())
+    y = g_randn(T, d, seed=38).bfloat16(); t = g_randn(T, d, seed=39).bfloat16()
+    yr = torch.addcmul(y.float(), t.float(), mask).bfloat16()
+    L.fma_mask_bf16(y, t, mask)
+    assert torch.equal(y, yr) or rel_err(y, yr) < 1e-3
+
+
 def test_gemm_device_side_limits():
     """m_count / k_count (the heads' masked-row count, read on the device): rows beyond the
     rounded count stay untouched, the K range is cut, empty split-K slices contribute zero."""
