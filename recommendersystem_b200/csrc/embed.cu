@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(128) segment_reduce_kernel(const float* __rest
 // other (8 in flight per thread) instead of a dependent walk over the chunks.  Four
 // thread groups take contiguous quarters of the pieces and are combined in group order:
 // the order of additions is a pure function of idx -> bitwise reproducible.
-constexpr int FIX_GROUPS = 4;
+constexpr int FIX_GROUPS = 1;  // >1: that many thread groups split a run's pieces (only pays for runs of thousands of tokens)
 __global__ void __launch_bounds__(128 * FIX_GROUPS) segment_fixup_kernel(const int32_t* __restrict__ keys, long long n, int d,
                                                                          float* __restrict__ table,
                                                                          const float* __restrict__ head,
@@ -416,16 +416,16 @@ __global__ void __launch_bounds__(128 * FIX_GROUPS) segment_fixup_kernel(const i
   const long long i0 = grp * per, i1 = min(m, i0 + per);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (col < d) {
-    for (long long i = i0; i < i1; i += 8) {
-      float4 v[8];
+    for (long long i = i0; i < i1; i += 16) {
+      float4 v[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < 16; ++u)
         if (i + u < i1) {
           const float* src = (i + u == 0) ? tail + c * d : head + (c + i + u) * d;
           v[u] = ldg_stream(reinterpret_cast<const float4*>(src + col));
         }
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < 16; ++u)
         if (i + u < i1) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
     }
   }
