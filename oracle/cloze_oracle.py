@@ -159,7 +159,7 @@ def rope(x, cos, sin):
     return torch.stack((a * c - b * s, a * s + b * c), dim=-1).flatten(3).type_as(x)
 
 
-def attention(x, p, pre, config, vis, cos, sin, drop=None):
+def attention(x, p, pre, config, vis, cos, sin, drop=None, run_len=None):
     """transformer.model.py:256-286: softmax attention, scale 1/sqrt(hd); in finetune mode
     LoRA r=8, alpha=16 on q and v (:235-254, 263-271).  `drop` = (mask_q, mask_v) multiplies
     the LoRA input like nn.Dropout(0.1) in training (masks already scaled by 1/0.9); None = eval."""
@@ -175,10 +175,35 @@ def attention(x, p, pre, config, vis, cos, sin, drop=None):
         v = v + F.linear(F.linear(xv, p[pre + "v_proj_lora_A.weight"]), p[pre + "v_proj_lora_B.weight"]) * 2.0
     q, v = q.view(B, T, H, hd), v.view(B, T, G, hd)
     q, k = rope(q, cos, sin), rope(k, cos, sin)
-    o = F.scaled_dot_product_attention(
-        q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), attn_mask=vis[:, None], enable_gqa=H != G
-    )
+    if config.get("attention", "softmax") == "silu":
+        o = silu_pointwise_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), vis, run_len)
+    else:
+        o = F.scaled_dot_product_attention(
+            q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), attn_mask=vis[:, None], enable_gqa=H != G
+        )
     return F.linear(o.transpose(1, 2).reshape(B, T, H * hd), p[pre + "output_proj.weight"])
+
+
+def run_lengths(userid):
+    """Tokens in each token's user run, [B, 2S] (item + action token per position)."""
+    u = userid.repeat_interleave(2, dim=1)
+    return (u[:, :, None] == u[:, None, :]).sum(-1)
+
+
+def silu_pointwise_attention(q, k, v, vis, run_len):
+    """BASELINE configs[2] variant, NOT in the reference (README.md:6 only cites HSTU, arXiv 2402.17152):
+    point-wise attention out_t = sum_s silu(q_t.k_s / sqrt(hd)) / n_t * v_s over the reference's visibility
+    (same user run, token-mask rule), n_t = number of tokens of t's user run (HSTU's 1/n), no softmax.
+    q [B,H,T,hd], k/v [B,G,T,hd]; scores and silu in fp32, the weights are cast to q's dtype before the
+    value product (as the probabilities of a fused kernel are).  Reference-unpinned: this function is the
+    definition the CUDA kernels are held to."""
+    B, H, T, hd = q.shape
+    G = k.shape[1]
+    k, v = k.repeat_interleave(H // G, 1), v.repeat_interleave(H // G, 1)
+    s = (q.float() @ k.float().transpose(-1, -2)) / math.sqrt(hd)
+    n = run_len.clamp(min=1).to(torch.float32)  # [B,T]
+    a = torch.where(vis[:, None], F.silu(s), torch.zeros_like(s)) / n[:, None, :, None]
+    return (a.to(q.dtype) @ v).to(q.dtype)
 
 
 def swiglu(x, p, pre):
@@ -186,7 +211,7 @@ def swiglu(x, p, pre):
     return F.linear(F.silu(F.linear(x, p[pre + "w1.weight"])) * F.linear(x, p[pre + "w3.weight"]), p[pre + "w2.weight"])
 
 
-def trunk(x, p, config, vis, positions=None, taps=None, drops=None):
+def trunk(x, p, config, vis, positions=None, taps=None, drops=None, run_len=None):
     """transformer.model.py:297-343: pre-norm residual blocks + final norm.
     RoPE positions are token indices inside the row unless given (:336-339)."""
     T = x.shape[1]
@@ -200,7 +225,7 @@ def trunk(x, p, config, vis, positions=None, taps=None, drops=None):
     for i in range(config["num_layers"]):
         pre = f"transformers.layers.{i}."
         x = x + attention(rms_norm(x, p[pre + "sa_norm.scale"]), p, pre + "attn.", config, vis, cos, sin,
-                          drop=None if drops is None else drops[i])
+                          drop=None if drops is None else drops[i], run_len=run_len)
         x = x + swiglu(rms_norm(x, p[pre + "mlp_norm.scale"]), p, pre + "mlp.")
         if taps is not None:
             taps[f"layer{i}"] = x
@@ -251,7 +276,7 @@ def step(d, p, config, randval, evaluate=False, taps=None, drops=None):
     vis = visibility(dm["userid"], dm["token_mask_ids"])
     if taps is not None:
         taps["x0"] = x0
-    hidden = trunk(x0, p, config, vis, taps=taps, drops=drops)
+    hidden = trunk(x0, p, config, vis, taps=taps, drops=drops, run_len=run_lengths(dm["userid"]))
     if taps is not None:
         taps["hidden"] = hidden
     return cloze_losses(hidden, dm, p, config, evaluate), dm
@@ -266,7 +291,7 @@ def inference_forward(d, p, config, task):
     if "rope_input_pos" in d:
         rp = d["rope_input_pos"]
         pos = torch.stack((2 * rp, 2 * rp + 1), dim=2).reshape(rp.shape[0], -1)
-    e = trunk(x0, p, config, vis, positions=pos)
+    e = trunk(x0, p, config, vis, positions=pos, run_len=run_lengths(d["userid"]))
     if task == "retrieval":
         return e
     assert task == "ranking"

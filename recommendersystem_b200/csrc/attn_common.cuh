@@ -16,6 +16,7 @@ struct AttnDev {
   __nv_bfloat16* out; float* lse2;          // fwd outputs
   const float* delta;                        // bwd
   __nv_bfloat16* dqkv; long long ld;         // bwd output (layout of qkv)
+  int mode;                                  // 0 softmax, 1 point-wise SiLU (pair kernels only)
 };
 
 // byte offset of (row, 16-byte chunk) inside a [rows x 128 B] SW128 K-major tile

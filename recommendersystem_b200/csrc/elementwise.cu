@@ -201,7 +201,7 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, long long T, long l
 }
 
 // ----------------------------------------------------------------- SwiGLU ---
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }  // same formula as the fused GEMM epilogue
+__device__ __forceinline__ float silu_f(float x) { return silu_fast(x); }  // same formula as the fused GEMM epilogue
 
 __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ act, long long T, int I) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

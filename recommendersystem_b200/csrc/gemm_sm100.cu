@@ -72,8 +72,7 @@ __device__ __forceinline__ void decode_tile(const GemmDev& p, int tile, int& m_b
   n_blk = r / gm;
 }
 
-// x * sigmoid(x); approximate divide (MUFU.RCP path): the result is rounded to bf16 anyway
-__device__ __forceinline__ float silu_f32(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_f32(float x) { return silu_fast(x); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 // One accumulator row (thread) x 32 columns, already in registers.

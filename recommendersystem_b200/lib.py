@@ -54,7 +54,7 @@ class AttnArgs(C.Structure):
     _fields_ = [
         ("qkv", vp), ("ld", i64), ("k_col", C.c_int), ("v_col", C.c_int),
         ("H", C.c_int), ("G", C.c_int), ("rows", C.c_int), ("row_len", C.c_int),
-        ("tm_tok", vp), ("seg_start", vp), ("seg_end", vp),
+        ("tm_tok", vp), ("seg_start", vp), ("seg_end", vp), ("mode", C.c_int),
     ]
 
 
@@ -322,11 +322,15 @@ def check_rows(userid_bs):
     return bad
 
 
-def attn_args(qkv, H, G, rows, row_len, tm_tok, seg_s, seg_e):
+ATTN_SOFTMAX, ATTN_SILU = 0, 1
+
+
+def attn_args(qkv, H, G, rows, row_len, tm_tok, seg_s, seg_e, mode=ATTN_SOFTMAX):
     a = AttnArgs()
     a.qkv, a.ld, a.k_col, a.v_col = vp(qkv.data_ptr()), qkv.shape[1], H * 64, (H + G) * 64
     a.H, a.G, a.rows, a.row_len = H, G, rows, row_len
     a.tm_tok, a.seg_start, a.seg_end = ptr(tm_tok), ptr(seg_s), ptr(seg_e)
+    a.mode = mode
     return a
 
 

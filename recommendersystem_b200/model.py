@@ -201,6 +201,14 @@ class _Params:
         self.index = {n: i for i, n in enumerate(self.names)}
 
 
+def _attn_mode(cfg):
+    """config["attention"]: "softmax" (the reference, default) or "silu" (HSTU-style point-wise attention,
+    BASELINE configs[2]; not in the reference - defined by oracle/cloze_oracle.py:silu_pointwise_attention)."""
+    kind = cfg.get("attention", "softmax")
+    assert kind in ("softmax", "silu"), kind
+    return L.ATTN_SILU if kind == "silu" else L.ATTN_SOFTMAX
+
+
 def _bf16(shape, dev):
     return torch.empty(shape, dtype=torch.bfloat16, device=dev)
 
@@ -323,7 +331,7 @@ class _ClozeStep(torch.autograd.Function):
                 L.rope(qkv, H + G, 2 * S, cos, sin)
                 lora = (aq, av, xq, xv, mq, mv)
             ao = _bf16((T, H * 64), dev); lse = _f32((H, T), dev)
-            at = L.attn_args(qkv, H, G, B, 2 * S, tm_tok, seg_s, seg_e)
+            at = L.attn_args(qkv, H, G, B, 2 * S, tm_tok, seg_s, seg_e, mode=_attn_mode(cfg))
             L.attn_fwd(at, ao, lse)
             dl1 = _bf16((T, dm), dev)
             L.gemm(ao, o_w, dl1, T, dm, H * 64)
@@ -524,7 +532,7 @@ class _ClozeStep(torch.autograd.Function):
                 L.gemm(dh16, ao, g_o, dm, H * 64, T, a_kmajor=False, lda=dm, b_kmajor=False, ldb=H * 64, epilogue=L.EPI_F32,
                        split_k=-1)
             dqkv = _bf16((T, QKV), dev); delta = _f32((H, T), dev)
-            at = L.attn_args(qkv, H, G, B, 2 * S, tm_tok, seg_s, seg_e)
+            at = L.attn_args(qkv, H, G, B, 2 * S, tm_tok, seg_s, seg_e, mode=_attn_mode(cfg))
             L.attn_bwd(at, ao, dao, lse, dqkv, delta)
             L.rope(dqkv, H + G, 2 * S, cos, sin, inverse=True)
             dxn = dhn  # reuse
@@ -639,7 +647,7 @@ def _inference_hidden(model, d):
             L.rmsnorm_fwd(h, W[f"l{i}.san"], xn, None, None, delta=dl, h_out=x)  # x = h + mlp(h)
         first = False
         L.gemm(xn, qkv_w, qkv, T, QKV, dm, epilogue=L.EPI_ROPE, rope=rope)
-        L.attn_fwd(L.attn_args(qkv, H, G, B, 2 * S, tm_tok, seg_s, seg_e), ao, lse)
+        L.attn_fwd(L.attn_args(qkv, H, G, B, 2 * S, tm_tok, seg_s, seg_e, mode=_attn_mode(cfg)), ao, lse)
         L.gemm(ao, o_w, dl, T, dm, H * 64)
         L.rmsnorm_fwd(x, W[f"l{i}.mln"], xn, None, None, delta=dl, h_out=h)      # h = x + attn(x)
         L.gemm(xn, w13, gu, T, 2 * I, dm, epilogue=L.EPI_SWIGLU, aux=act, ldaux=I)

@@ -277,6 +277,40 @@ def attn_reference(qkv, uid, tm, rows, row_len, H, G):
     return o.transpose(1, 2).reshape(T, H * 64), torch.logsumexp(s, -1)  # lse [rows,H,row_len]
 
 
+def attn_reference_silu(qkv, uid, tm, rows, row_len, H, G):
+    """oracle.silu_pointwise_attention on the fused qkv layout (fp32 autograd reference)."""
+    from oracle.cloze_oracle import run_lengths, silu_pointwise_attention, visibility
+    T = rows * row_len
+    q = qkv[:, :H * 64].reshape(rows, row_len, H, 64).transpose(1, 2)
+    k = qkv[:, H * 64:(H + G) * 64].reshape(rows, row_len, G, 64).transpose(1, 2)
+    v = qkv[:, (H + G) * 64:].reshape(rows, row_len, G, 64).transpose(1, 2)
+    o = silu_pointwise_attention(q, k, v, visibility(uid, tm), run_lengths(uid))
+    return o.transpose(1, 2).reshape(T, H * 64)
+
+
+@pytest.mark.parametrize("rows,row_len,H,G,long_runs", [(2, 128, 2, 1, False), (3, 512, 4, 2, False), (2, 1024, 4, 2, True)])
+def test_attention_silu_pointwise_fwd_bwd(rows, row_len, H, G, long_runs):
+    """BASELINE configs[2] attention variant against its definition in the oracle (reference-unpinned)."""
+    uid, tm, qkv = make_attn_case(rows, row_len, H, G, seed=11 + rows, long_runs=long_runs)
+    T = rows * row_len
+    seg_s, seg_e = L.token_segments(uid)
+    tm_tok = torch.empty(T, dtype=torch.int32, device=DEV); L.interleave_i32(tm.reshape(-1), tm_tok)
+    at = L.attn_args(qkv, H, G, rows, row_len, tm_tok, seg_s, seg_e, mode=L.ATTN_SILU)
+    out = torch.empty(T, H * 64, device=DEV, dtype=torch.bfloat16); lse = torch.empty(H, T, device=DEV)
+    L.attn_fwd(at, out, lse)
+    x = qkv.float().requires_grad_(True)
+    ref = attn_reference_silu(x, uid, tm, rows, row_len, H, G)
+    live = (uid.repeat_interleave(2, 1).reshape(-1) >= 0)
+    report("silu attn out", out[live], ref[live].detach(), 1e-2)
+    dout = (g_randn(T, H * 64, seed=5) * 0.5).bfloat16()
+    ref.backward(dout.float())
+    dqkv = torch.empty_like(qkv); delta = torch.empty(H, T, device=DEV)
+    L.attn_bwd(at, out, dout, lse, dqkv, delta)
+    report("silu attn dq", dqkv[:, :H * 64], x.grad[:, :H * 64], 2e-2)
+    report("silu attn dk", dqkv[:, H * 64:(H + G) * 64], x.grad[:, H * 64:(H + G) * 64], 2e-2)
+    report("silu attn dv", dqkv[:, (H + G) * 64:], x.grad[:, (H + G) * 64:], 2e-2)
+
+
 @pytest.mark.parametrize("rows,row_len,H,G,long_runs", [(2, 128, 2, 1, False), (3, 512, 4, 2, False), (2, 1024, 2, 2, True)])
 def test_attention_fwd_bwd(rows, row_len, H, G, long_runs):
     uid, tm, qkv = make_attn_case(rows, row_len, H, G, seed=rows * 7 + H, long_runs=long_runs)

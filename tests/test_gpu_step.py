@@ -167,6 +167,16 @@ def test_c3_rating_only_task_weights():
     _oracle_vs_cuda(cfg, rows, batch, tw, seed=3)
 
 
+def test_c3_hstu_silu_attention_rating_model():
+    """BASELINE configs[2] as named: point-wise SiLU attention (config["attention"] = "silu") + regression head,
+    rating-only objective.  The reference has no such attention: the oracle's own definition is the check."""
+    from oracle.cloze_oracle import default_task_weights
+    from recommendersystem_b200.synthetic import make_batches, make_config
+    cfg, rows = make_config("C1", num_layers=2, attention="silu")
+    batch = make_batches(cfg, rows, 1, seed=4)[0]
+    _oracle_vs_cuda(cfg, rows, batch, default_task_weights(finetune_metric="rating"), seed=7)
+
+
 def test_c5_short_histories_scatter_stress():
     """BASELINE configs[4]: short recent-history users packed back to back (hundreds of user runs per
     row batch), Zipf 1.2 items: heavy duplicate rows in the table gradient (pre-train mode, tables train)."""

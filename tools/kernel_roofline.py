@@ -112,6 +112,11 @@ def main():
     rstd = torch.empty(T, device=dev)
     ms = timer(lambda: L.rmsnorm_fwd(x, scale, y16, None, rstd))
     rec("rmsnorm_fwd", ms, bytes_=T * d * (4 + 2) + T * 4)
+    dlt = torch.randn((T, d), device=dev, generator=g).bfloat16()
+    hsum = torch.empty((T, d), device=dev)
+    ms = timer(lambda: L.rmsnorm_fwd(x, scale, y16, None, rstd, delta=dlt, h_out=hsum))
+    rec("rmsnorm_fwd + fused residual add", ms, bytes_=T * d * (4 + 2 + 4 + 2) + T * 4)
+    del dlt, hsum
     dy16 = torch.randn((T, d), device=dev, generator=g).bfloat16()
     dres = torch.randn((T, d), device=dev, generator=g)
     dx = torch.empty((T, d), device=dev)
@@ -160,6 +165,20 @@ def main():
 
     gemm_case("gemm qkv proj", T, QKV, d)
     gemm_case("gemm w1|w3 (gate,up)", T, 2 * I, d)
+    # the fused epilogues the step actually uses
+    A = (torch.randn((T, d), device=dev, generator=g) * 0.1).bfloat16()
+    Wg = (torch.randn((2 * I, d), device=dev, generator=g) * 0.1).bfloat16()
+    gu_f = torch.empty((T, 2 * I), dtype=torch.bfloat16, device=dev); act_f = torch.empty((T, I), dtype=torch.bfloat16, device=dev)
+    ms = timer(lambda: L.gemm(A, Wg, gu_f, T, 2 * I, d, epilogue=L.EPI_SWIGLU, aux=act_f, ldaux=I))
+    rec("gemm w1|w3 + fused SwiGLU epilogue", ms, flops=2.0 * T * 2 * I * d, note=f"{T}x{2 * I}x{d}, writes gu and act")
+    Wq = (torch.randn((QKV, d), device=dev, generator=g) * 0.1).bfloat16()
+    qkv_f = torch.empty((T, QKV), dtype=torch.bfloat16, device=dev)
+    inv = 1.0 / (500000.0 ** (torch.arange(0, 64, 2).float() / 64))
+    ang = torch.outer(torch.arange(2 * S).float(), inv)
+    cosb, sinb = torch.cos(ang).to(dev).contiguous(), torch.sin(ang).to(dev).contiguous()
+    ms = timer(lambda: L.gemm(A, Wq, qkv_f, T, QKV, d, epilogue=L.EPI_ROPE, rope=dict(cos=cosb, sin=sinb, cols=(H + G) * 64, row_len=2 * S)))
+    rec("gemm qkv proj + fused RoPE epilogue", ms, flops=2.0 * T * QKV * d, note=f"{T}x{QKV}x{d}")
+    del A, Wg, gu_f, act_f, Wq, qkv_f
     gemm_case("gemm w2 (down)", T, d, I)
     gemm_case("gemm out proj", T, d, H * 64)
     # dW shape: [2I, T] x [T, d], MN-major operands, split-K
