@@ -16,6 +16,21 @@ import torch.distributed as dist
 from . import lib as L
 
 
+def wsd_lr_factor(step, warmup_steps, total_steps, decay_ratio=0.1, final_ratio=0.1):
+    """Warm-up / stable / decay multiplier of the reference's pre-train schedule (transformer.py:310-328
+    WSDScheduler, used as LambdaLR at :344-347: warm-up 2000 steps, last 10 % decays linearly to 0.1x).
+    `step` counts scheduler.step() calls, as LambdaLR passes it."""
+    decay_steps = int(total_steps * decay_ratio)
+    stable_steps = total_steps - warmup_steps - decay_steps
+    assert stable_steps >= 0
+    s = max(0, min(int(step), total_steps))
+    if s <= warmup_steps:
+        return s / max(1, warmup_steps)
+    if s <= warmup_steps + stable_steps:
+        return 1.0
+    return 1.0 - (1.0 - final_ratio) * (s - warmup_steps - stable_steps) / max(1, decay_steps)
+
+
 class FlatAdamW:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1, max_grad_norm=1.0):
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
@@ -73,6 +88,19 @@ class FlatAdamW:
         L.adamw(self.flat_p[:nd], self.flat_g[:nd], self.m[:nd], self.v[:nd], lr, b1, b2, self.eps, self.wd, self.steps, self._scale)
         if nd < self.flat_p.numel():
             L.adamw(self.flat_p[nd:], self.flat_g[nd:], self.m[nd:], self.v[nd:], lr, b1, b2, self.eps, 0.0, self.steps, self._scale)
+
+    def set_schedule(self, warmup_steps, total_steps, decay_ratio=0.1, final_ratio=0.1):
+        """Pre-train WSD schedule (transformer.py:344-347); finetune keeps the constant factor 1 (:331-332)."""
+        self._sched = (warmup_steps, total_steps, decay_ratio, final_ratio)
+        self._sched_step = 0
+
+    def scheduled_step(self):
+        """optimizer.step(); scheduler.step() of transformer.py:274-276: the n-th call uses the factor of step n-1."""
+        f = wsd_lr_factor(self._sched_step, *self._sched) if getattr(self, "_sched", None) else 1.0
+        self.step(lr=self.lr * f)
+        if getattr(self, "_sched", None):
+            self._sched_step += 1
+        return f
 
     def grad_norm(self):
         """Global L2 norm of the rank-averaged gradient of the last step (device tensor)."""

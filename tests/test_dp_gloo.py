@@ -91,3 +91,27 @@ def test_block_shuffle_moves_whole_users():
     assert np.array_equal(d["matchedid"], ref) and np.array_equal(d["userid"], u[ref])
     w = list(packer.windows({"userid": np.zeros(64, np.int32)}, 16))
     assert len(w) == 4 and all(len(x["userid"]) == 16 for x in w)
+
+
+def test_wsd_schedule_matches_reference_formula():
+    """transformer.py:310-328 restated literally next to optim.wsd_lr_factor."""
+    from recommendersystem_b200.optim import wsd_lr_factor
+
+    class WSD:  # the reference class, verbatim semantics
+        def __init__(self, warmup_steps, total_steps, decay_ratio, final_ratio):
+            self.warmup_steps, self.total_steps, self.final_ratio = warmup_steps, total_steps, final_ratio
+            self.decay_steps = int(total_steps * decay_ratio)
+            self.stable_steps = total_steps - warmup_steps - self.decay_steps
+
+        def __call__(self, step):
+            s = max(0, min(int(step), self.total_steps))
+            if s <= self.warmup_steps:
+                return s / max(1, self.warmup_steps)
+            if s <= (self.warmup_steps + self.stable_steps):
+                return 1.0
+            return 1.0 - (1.0 - self.final_ratio) * (s - self.warmup_steps - self.stable_steps) / max(1, self.decay_steps)
+
+    for w, t in ((2000, 50000), (10, 37), (0, 5)):
+        ref = WSD(w, t, 0.1, 0.1)
+        for s in list(range(0, min(t, 60))) + [t // 2, t - 3, t - 1, t, t + 5]:
+            assert wsd_lr_factor(s, w, t) == ref(s), (w, t, s)

@@ -217,3 +217,31 @@ def test_c2_full_size_properties():
     assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
     assert torch.isfinite(outs[0][1]).all() and float(outs[0][1][-1].abs().sum()) > 0   # mask row gets the masked tokens' gradient
     assert int((d["matchedid"] == -1).sum()) == int((rv < cfg["mask_rate"]).sum())
+
+
+def test_step_tail_matches_torch_adamw_and_clip():
+    """SURVEY.md 8 row a20 (transformer.py:272-276, 285-298): FlatAdamW on the flat buffers == clip_grad_norm_(1.0) +
+    torch.optim.AdamW(fused, betas .9/.95, wd .1 on dim>=2) + the WSD LambdaLR on the same gradients, over several steps."""
+    import copy
+    from recommendersystem_b200.optim import FlatAdamW, wsd_lr_factor
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(96, 200), torch.nn.GELU(), torch.nn.Linear(200, 7)).to(DEV)
+    ref = copy.deepcopy(net)
+    decay = [p for p in ref.parameters() if p.dim() >= 2]; nodecay = [p for p in ref.parameters() if p.dim() < 2]
+    topt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.1}, {"params": nodecay, "weight_decay": 0.0}], lr=3e-3,
+                             betas=(0.9, 0.95), fused=True)
+    opt = FlatAdamW(net, lr=3e-3)
+    opt.set_schedule(warmup_steps=2, total_steps=6)
+    sched = torch.optim.lr_scheduler.LambdaLR(topt, lambda s: wsd_lr_factor(s, 2, 6))
+    for step in range(6):
+        x = torch.randn(64, 96, device=DEV, generator=torch.Generator(device=DEV).manual_seed(step)) * (4.0 if step % 2 else 0.2)
+        for m in (net, ref):
+            loss = m(x).square().mean() * (50.0 if step % 2 else 1.0)   # alternate clipped / unclipped steps
+            loss.backward()
+        gn_ref = torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+        topt.step(); topt.zero_grad(); sched.step()
+        opt.scheduled_step()
+        assert abs(float(opt.grad_norm()) - float(gn_ref)) <= 1e-5 * float(gn_ref)
+        opt.zero_grad()
+        for a, b in zip(net.parameters(), ref.parameters()):
+            assert float((a - b).abs().max()) <= 2e-6 * max(1.0, float(b.abs().max())), step
