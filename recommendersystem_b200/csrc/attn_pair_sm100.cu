@@ -21,6 +21,20 @@ namespace graft {
 constexpr int PAIR_THREADS = 544;
 
 __device__ __forceinline__ void head_sync(int h) { asm volatile("bar.sync %0, 256;" ::"r"(h + 1) : "memory"); }
+// the same barrier, returning the OR of `flag` over the head's 256 threads
+__device__ __forceinline__ bool head_sync_or(int h, bool flag) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %2, 0;\n\t"
+      "bar.red.or.pred p, %1, 256, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(r)
+      : "r"(h + 1), "r"((uint32_t)flag)
+      : "memory");
+  return r != 0;
+}
+constexpr float kExpClamp = 120.f;  // log2 units above the row's reference: unreachable (|q.k| gap > 660), keeps exp2 finite
 
 // ================================================================ forward =====
 // smem: Q 2x16K | K 2x16K | V 2x16K | P 2x32K | mask ids [2 h][2 st][128] | Z [2][2][4] |
@@ -65,7 +79,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p)
     tma_prefetch_desc(&tmQKV);
     mbar_init(bar_q, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_k[i], 1); mbar_init(&bar_v[i], 1); mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 256); mbar_init(&bar_pv[i], 1);
+      mbar_init(&bar_k[i], 1); mbar_init(&bar_v[i], 1); mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); mbar_init(&bar_pv[i], 1);
     }
     fence_barrier_init();
   }
@@ -127,7 +141,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p)
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma_bf16(tmem + 256 + h * 64, umma_desc_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024),
-                      umma_desc_sw128(va + k * 2048, 16384, 1024), idesc_pv, k > 0);
+                      umma_desc_sw128(va + k * 2048, 16384, 1024), idesc_pv, (k > 0 || j > 0) ? 1u : 0u);  // O accumulates in TMEM
           umma_commit(&bar_pv[h]);
         }
         if (j + 2 < n_kv) {  // refill stage st with tile j+2: its S MMAs retired (bar_p seen), wait for its PV MMAs
@@ -156,14 +170,17 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p)
     uint32_t* sZh = sZ + hh * 8;
     float* sXmine = sX + (hh * 2 + half) * 128;
     float* sXother = sX + (hh * 2 + (half ^ 1)) * 128;
-    float o[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) o[c] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+    // Fixed-reference softmax: a row's stabiliser m_ref is the maximum over its run's columns in the FIRST
+    // key tile that holds any of them and is never changed afterwards (softmax is invariant to the
+    // reference; later scores may exceed it - their exponentials are > 1, harmless in bf16 / fp32 - and the
+    // exponent is clamped far beyond any reachable score gap).  Consequences: the accumulator is never
+    // rescaled, so P.V accumulates across key tiles inside TMEM and is read once at the end, and S is read
+    // once per tile.  The two-pass tile (row max, exchange between the two column halves) only runs while
+    // some row of the head has no reference yet - decided head-wide by one reducing barrier per tile.
+    float m_ref = SILU ? 0.f : -INFINITY, l_run = 0.f;
     const float inv_n = 1.f / (float)max(qe - qs, 1);
 
-    // mask ids of a tile's keys are staged one tile ahead; the per-tile head barrier (row max
-    // exchange) also publishes them
+    // mask ids of a tile's keys are staged one tile ahead; the per-tile head barrier also publishes them
     int tk_next = 0;
     auto load_ids = [&](int jj) {  // issue the global load early ...
       if (half == 0 && jj < n_kv) tk_next = p.tm[row_base + (long long)(kv_lo + jj) * 128 + t];
@@ -177,11 +194,12 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p)
     };
     load_ids(0);
     publish_ids(0);
-    head_sync(hh);
 
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
       const int tile0 = (kv_lo + j) * 128;
+      // barrier of the head's 256 threads: publishes tile j's mask ids and ORs "this row has no reference yet"
+      const bool any_need = head_sync_or(hh, !SILU && m_ref == -INFINITY);
       load_ids(j + 1);
       uint32_t vw[2], rw[2];
       {
@@ -196,14 +214,13 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p)
       }
       mbar_wait(&bar_s[hh], j & 1);
       tc_fence_after();
-      // row max over the run's columns (a superset of the visible ones: any upper bound of the
-      // visible scores stabilises the softmax identically, and only run edges need a select)
-      float mx = -INFINITY;
-      if (!SILU) {
+      if (any_need) {
+        // row max over the run's columns (a superset of the visible ones: any finite reference works)
+        float mx = -INFINITY;
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
           const uint32_t w = rw[c2];
-          if (!__any_sync(0xffffffffu, vw[c2] != 0u)) continue;
+          if (!__any_sync(0xffffffffu, w != 0u)) continue;
           float s[32];
           tmem_ld_32x32_f(t_s + c2 * 32, s);
           if (__all_sync(0xffffffffu, w == 0xffffffffu)) {
@@ -214,22 +231,18 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p)
             for (int c = 0; c < 32; ++c) mx = fmaxf(mx, (w >> c) & 1u ? s[c] : -INFINITY);
           }
         }
+        sXmine[t] = mx;
+        head_sync(hh);
+        mx = fmaxf(mx, sXother[t]);
+        if (m_ref == -INFINITY) m_ref = mx;  // still -inf when the row has no column in this tile
+        head_sync(hh);                       // the exchange slots are rewritten by the next two-pass tile
       }
-      sXmine[t] = mx;
       publish_ids(j + 1);
-      head_sync(hh);
-      mx = SILU ? 0.f : fmaxf(fmaxf(mx, sXother[t]), m_run);
-      // deferred O update of the previous tile: its PV MMA was issued before this tile's S
-      if (j > 0) {
+      if (j > 0) {  // P_h is single-buffered: the PV MMA of the previous tile must have read it
         mbar_wait(&bar_pv[hh], (j - 1) & 1);
         tc_fence_after();
-        float v[32];
-        tmem_ld_32x32_f(t_pv, v);
-#pragma unroll
-        for (int c = 0; c < 32; ++c) o[c] = fmaf(o[c], alpha_prev, v[c]);
       }
-      const float alpha = SILU ? 1.f : ((m_run == -INFINITY) ? 0.f : ex2((m_run - mx) * kScaleLog2));
-      const float mscaled = (mx == -INFINITY) ? 0.f : mx * kScaleLog2;
+      const float mscaled = (m_ref == -INFINITY) ? 0.f : m_ref * kScaleLog2;
       float lsum = 0.f;
 #pragma unroll
       for (int c2 = 0; c2 < 2; ++c2) {
@@ -247,16 +260,16 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p)
             if (__all_sync(0xffffffffu, wb == 0xffu)) {
 #pragma unroll
               for (int c = 8 * g8; c < 8 * g8 + 8; c += 2) {
-                const float p0 = SILU ? silu_fast(s[c] * kScale) * inv_n : ex2(fmaf(s[c], kScaleLog2, -mscaled));
-                const float p1 = SILU ? silu_fast(s[c + 1] * kScale) * inv_n : ex2(fmaf(s[c + 1], kScaleLog2, -mscaled));
+                const float p0 = SILU ? silu_fast(s[c] * kScale) * inv_n : ex2(fminf(fmaf(s[c], kScaleLog2, -mscaled), kExpClamp));
+                const float p1 = SILU ? silu_fast(s[c + 1] * kScale) * inv_n : ex2(fminf(fmaf(s[c + 1], kScaleLog2, -mscaled), kExpClamp));
                 lsum += p0 + p1;
                 pk[c >> 1] = pack_bf16(p0, p1);
               }
             } else {
 #pragma unroll
               for (int c = 8 * g8; c < 8 * g8 + 8; c += 2) {
-                const float e0 = SILU ? silu_fast(s[c] * kScale) * inv_n : ex2(fmaf(s[c], kScaleLog2, -mscaled));
-                const float e1 = SILU ? silu_fast(s[c + 1] * kScale) * inv_n : ex2(fmaf(s[c + 1], kScaleLog2, -mscaled));
+                const float e0 = SILU ? silu_fast(s[c] * kScale) * inv_n : ex2(fminf(fmaf(s[c], kScaleLog2, -mscaled), kExpClamp));
+                const float e1 = SILU ? silu_fast(s[c + 1] * kScale) * inv_n : ex2(fminf(fmaf(s[c + 1], kScaleLog2, -mscaled), kExpClamp));
                 const float p0 = (w >> c) & 1u ? e0 : 0.f;
                 const float p1 = (w >> (c + 1)) & 1u ? e1 : 0.f;
                 lsum += p0 + p1;
@@ -269,30 +282,25 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p)
         for (int q4 = 0; q4 < 4; ++q4)
           *reinterpret_cast<uint4*>(sPblk + sw128_off(t, c2 * 4 + q4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
       }
-      l_run = l_run * alpha + lsum;
-      m_run = mx;
-      alpha_prev = alpha;
+      l_run += lsum;
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(&bar_p[hh]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[hh]);  // one arrival per warp: 8 instead of 256 serialised updates of one mbarrier
     }
-    // last tile's O update, then normalise with the row sum of both halves
+    // the accumulated P.V of all tiles, then normalise with the row sum of both halves
     mbar_wait(&bar_pv[hh], (n_kv - 1) & 1);
     tc_fence_after();
-    {
-      float v[32];
-      tmem_ld_32x32_f(t_pv, v);
-#pragma unroll
-      for (int c = 0; c < 32; ++c) o[c] = fmaf(o[c], alpha_prev, v[c]);
-    }
-    head_sync(hh);            // everyone is past its last read of the max-exchange slots
+    float o[32];
+    tmem_ld_32x32_f(t_pv, o);
+    head_sync(hh);            // everyone is past its last read of the exchange slots
     sXmine[t] = l_run;
     head_sync(hh);
     const float l_tot = l_run + sXother[t];
     const float inv = SILU ? 1.f : (l_tot > 0.f ? 1.f / l_tot : 0.f);
     __nv_bfloat16* orow = p.out + tq * (long long)(p.H * 64) + h * 64 + half * 32;
     store_row_bf16_32(orow, o, inv);
-    if (half == 0) p.lse2[(long long)h * p.T + tq] = (!SILU && l_tot > 0.f) ? (m_run * kScaleLog2 + log2f(l_tot)) : 0.f;
+    if (half == 0) p.lse2[(long long)h * p.T + tq] = (!SILU && l_tot > 0.f) ? (m_ref * kScaleLog2 + log2f(l_tot)) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -341,7 +349,7 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
   if (tid == 512) {
     mbar_init(bar_q, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_kv[i], 1); mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 256); mbar_init(&bar_dq[i], 1);
+      mbar_init(&bar_kv[i], 1); mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); mbar_init(&bar_dq[i], 1);
     }
     fence_barrier_init();
   }
@@ -491,7 +499,8 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
         *reinterpret_cast<uint4*>(sDSh + sw128_off(t, half * 4 + q4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(&bar_p[hh]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[hh]);  // one arrival per warp: 8 instead of 256 serialised updates of one mbarrier
     }
     mbar_wait(&bar_dq[hh], (n_kv - 1) & 1);
     tc_fence_after();
@@ -546,7 +555,7 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
   if (tid == 512) {
     mbar_init(bar_k, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&bar_q[i], 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 256); mbar_init(&bar_acc[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); mbar_init(&bar_acc[i], 1); }
     fence_barrier_init();
   }
   if (warp == 16) tmem_alloc<512>(tmem_slot);
@@ -716,7 +725,8 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
       }
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(&bar_p[hh]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[hh]);  // one arrival per warp: 8 instead of 256 serialised updates of one mbarrier
     }
     // both slots' accumulate MMAs must have retired; slot 0 stores dV, slot 1 stores dK
     mbar_wait(&bar_acc[0], (n_it - 1) & 1);

@@ -155,6 +155,17 @@ def main():
     ms = timer(lambda: L.attn_bwd(at, ao, dao, lse, dqkv, delta))
     rec("attention bwd (delta + dq + dkv)", ms, flops=2.5 * attn_flops)
 
+    # one user per row: every query tile visits all 16 key tiles (twice the tile steps of the jagged batch with the
+    # same number of CTAs) - separates the per-CTA fixed cost from the per-tile cost
+    uid1 = torch.arange(1, rows + 1, dtype=torch.int32, device=dev)[:, None].expand(rows, S).contiguous()
+    s1, e1 = L.token_segments(uid1)
+    at1 = L.attn_args(qkv, H, G, rows, 2 * S, tm, s1, e1)
+    dense_flops = 4.0 * H * 64 * rows * (2 * S) ** 2
+    ms = timer(lambda: L.attn_fwd(at1, ao, lse))
+    rec("attention fwd, one user per row (dense)", ms, flops=dense_flops, note="16 key tiles per query tile")
+    ms = timer(lambda: L.attn_bwd(at1, ao, dao, lse, dqkv, delta))
+    rec("attention bwd, one user per row (dense)", ms, flops=2.5 * dense_flops)
+
     # ------------------------------------------------------------------ GEMMs (tensor) ----
     def gemm_case(name, M, Nn, K, **kw):
         A = (torch.randn((M, K), device=dev, generator=g) * 0.1).bfloat16()
