@@ -82,6 +82,10 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p)
       mbar_init(&bar_k[i], 1); mbar_init(&bar_v[i], 1); mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); mbar_init(&bar_pv[i], 1);
     }
     fence_barrier_init();
+    // the Q tiles do not depend on the segment bounds: request them before the CTA-wide sync / TMEM allocation
+    mbar_expect_tx(bar_q, 32768);
+    tma_load_2d(sQ, &tmQKV, bar_q, h0 * 64, (int)(row_base + qt * 128));
+    tma_load_2d(sQ + 16384, &tmQKV, bar_q, (h0 + 1) * 64, (int)(row_base + qt * 128));
   }
   if (warp == 16) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
@@ -98,10 +102,6 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p)
       // ------------------------------------------------ issue thread ----------
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
-      const int q_row = (int)(row_base + qt * 128);
-      mbar_expect_tx(bar_q, 32768);
-      tma_load_2d(sQ, &tmQKV, bar_q, h0 * 64, q_row);
-      tma_load_2d(sQ + 16384, &tmQKV, bar_q, (h0 + 1) * 64, q_row);
       for (int s = 0; s < 2 && s < n_kv; ++s) {
         const int kr = (int)(row_base + (long long)(kv_lo + s) * 128);
         mbar_expect_tx(&bar_k[s], 16384);
@@ -352,6 +352,11 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
       mbar_init(&bar_kv[i], 1); mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); mbar_init(&bar_dq[i], 1);
     }
     fence_barrier_init();
+    mbar_expect_tx(bar_q, 65536);  // Q and dO tiles: independent of the segment bounds, requested first
+    for (int h = 0; h < 2; ++h) {
+      tma_load_2d(sQ + h * 16384, &tmQKV128, bar_q, (h0 + h) * 64, (int)(row_base + qt * 128));
+      tma_load_2d(sDO + h * 16384, &tmDO128, bar_q, (h0 + h) * 64, (int)(row_base + qt * 128));
+    }
   }
   if (warp == 16) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
@@ -367,12 +372,6 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);
-      const int q_row = (int)(row_base + qt * 128);
-      mbar_expect_tx(bar_q, 65536);
-      for (int h = 0; h < 2; ++h) {
-        tma_load_2d(sQ + h * 16384, &tmQKV128, bar_q, (h0 + h) * 64, q_row);
-        tma_load_2d(sDO + h * 16384, &tmDO128, bar_q, (h0 + h) * 64, q_row);
-      }
       for (int s = 0; s < 2 && s < n_kv; ++s) {
         const int kr = (int)(row_base + (long long)(kv_lo + s) * 64);
         mbar_expect_tx(&bar_kv[s], 16384);
@@ -557,6 +556,9 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
     for (int i = 0; i < 4; ++i) mbar_init(&bar_q[i], 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); mbar_init(&bar_acc[i], 1); }
     fence_barrier_init();
+    mbar_expect_tx(bar_k, 32768);  // this CTA's K and V tiles: requested before the sync / segment loads
+    tma_load_2d(sK, &tmQKV128, bar_k, p.k_col + g * 64, (int)(row_base + kt * 128));
+    tma_load_2d(sV, &tmQKV128, bar_k, p.v_col + g * 64, (int)(row_base + kt * 128));
   }
   if (warp == 16) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
@@ -573,10 +575,6 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 64, 0, 1);
-      const int k_row = (int)(row_base + kt * 128);
-      mbar_expect_tx(bar_k, 32768);
-      tma_load_2d(sK, &tmQKV128, bar_k, p.k_col + g * 64, k_row);
-      tma_load_2d(sV, &tmQKV128, bar_k, p.v_col + g * 64, k_row);
       auto load_q = [&](int w, int it) {
         const int st = it & 1;
         const int h = g * hpg + w + 2 * (it / n_q);
