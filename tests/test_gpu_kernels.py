@@ -506,6 +506,15 @@ def test_casts_colsum_select():
     k = int(cnt)
     assert k == nz.numel() and torch.equal(sel[:k].long(), nz) and torch.all(sel[k:] == -1)
     assert torch.equal(ws[:k], w[nz]) and torch.equal(ls[:k], lab[nz]) and torch.equal(ps[:k].long(), nz) and torch.all(ws[k:] == 0)
+    # ragged sizes (scalar tail, unaligned base) and more hits than slots
+    for n, cap, rate, off in ((4099, 64, 0.5, 1), (7, 16, 1.0, 0), (12289, 8192, 0.3, 3)):
+        wf = (torch.rand(n + off, generator=torch.Generator().manual_seed(n)) < rate).float().to(DEV)[off:]
+        lb = g_randn(n, seed=n); po = torch.arange(n, device=DEV, dtype=torch.int32)
+        sel, ws, ls, ps, cnt = L.select_rows(wf.contiguous() if off == 0 else wf, lb, po, cap)
+        nz = wf.nonzero().flatten()
+        k = min(int(cnt), cap)
+        assert int(cnt) == nz.numel() and torch.equal(sel[:k].long(), nz[:k]) and torch.all(sel[k:] == -1)
+        assert torch.equal(ls[:k], lb[nz[:k]])
 
 
 def test_rating_tail_and_adamw():
