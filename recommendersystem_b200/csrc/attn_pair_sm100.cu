@@ -20,6 +20,12 @@ namespace graft {
 
 constexpr int PAIR_THREADS = 544;
 __device__ unsigned int g_attn_work[4];  // work-item counters of the persistent kernels (zeroed before each launch)
+#ifdef ATTN_TRACE  /* diagnostic build: CTA 0 timestamps the events of its first 48 stream tiles (tools/attn_trace.py) */
+__device__ long long g_attn_trace[48 * 16];
+#define ATTN_EVT(tile, e) do { if (blockIdx.x == 0 && (tile) < 48) g_attn_trace[(tile) * 16 + (e)] = clock64(); } while (0)
+#else
+#define ATTN_EVT(tile, e) do { } while (0)
+#endif
 
 __device__ __forceinline__ void head_sync(int h) { asm volatile("bar.sync %0, 256;" ::"r"(h + 1) : "memory"); }
 // the same barrier, returning the OR of `flag` over the head's 256 threads
@@ -113,20 +119,29 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 16) {
-    if (lane == 0 && first_item >= 0) {
-      // ------------------------------------------------ issue thread ----------
+    if (first_item >= 0) {
+      // ------------------------------------------------ issue warp ------------
+      // The whole warp runs this control flow (one elected lane performs the TMA / MMA / barrier side effects):
+      // addresses and descriptors are then warp-uniform values the compiler keeps in uniform registers, which
+      // tcgen05.mma reads directly - a single divergent thread paid four R2UR moves (~100 clk) per MMA instead.
+      const bool leader = (lane == 0);
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
-      sItems[0] = first_item;          // ordinal 0 is blockIdx.x (published too, so every ring slot sees one arrival per
-      mbar_arrive(&bar_item[0]);       // ordinal and the waiters' phase is (k >> 2) & 1); ordinals >= 1 come from the counter
+      if (leader) {
+        sItems[0] = first_item;        // ordinal 0 is blockIdx.x (published too, so every ring slot sees one arrival per
+        mbar_arrive(&bar_item[0]);     // ordinal and the waiters' phase is (k >> 2) & 1); ordinals >= 1 come from the counter
+      }
       int fetched = 1;
       auto item_of = [&](int k) -> int {  // index of this CTA's k-th item (-1: no more work), drawing it if needed
         if (k == 0) return first_item;
         while (fetched <= k) {
-          int idx = (int)gridDim.x + (int)atomicAdd(work_counter, 1u);
-          if (idx >= n_items) idx = -1;
-          sItems[fetched & 3] = idx;
-          mbar_arrive(&bar_item[fetched & 3]);   // release: the softmax warps read the slot after their wait
+          if (leader) {
+            int idx = (int)gridDim.x + (int)atomicAdd(work_counter, 1u);
+            if (idx >= n_items) idx = -1;
+            sItems[fetched & 3] = idx;
+            mbar_arrive(&bar_item[fetched & 3]);   // release: the softmax warps read the slot after their wait
+          }
+          __syncwarp();
           ++fetched;
         }
         return sItems[k & 3];
@@ -134,9 +149,11 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
       auto load_q = [&](const FwdItem& it, int n) {  // item n's two Q tiles -> Q buffer n & 1
         uint8_t* q = sQ + (n & 1) * 32768;
         const int q_row = (int)(it.row_base + it.qt * 128);
-        mbar_expect_tx(&bar_q[n & 1], 32768);
-        tma_load_2d(q, &tmQKV, &bar_q[n & 1], it.h0 * 64, q_row);
-        tma_load_2d(q + 16384, &tmQKV, &bar_q[n & 1], (it.h0 + 1) * 64, q_row);
+        if (leader) {
+          mbar_expect_tx(&bar_q[n & 1], 32768);
+          tma_load_2d(q, &tmQKV, &bar_q[n & 1], it.h0 * 64, q_row);
+          tma_load_2d(q + 16384, &tmQKV, &bar_q[n & 1], (it.h0 + 1) * 64, q_row);
+        }
       };
       // K/V loads run two stream tiles ahead of the MMAs, through their own item cursor
       FwdItem ld = fwd_item(p, first_item);
@@ -153,13 +170,17 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
       };
       auto ld_k = [&]() {
         const int st = (int)(ld_g & 1);
-        mbar_expect_tx(&bar_k[st], 16384);
-        tma_load_2d(sK + st * 16384, &tmQKV, &bar_k[st], p.k_col + ld.g * 64, (int)(ld.row_base + (long long)(ld.kv_lo + ld_j) * 128));
+        if (leader) {
+          mbar_expect_tx(&bar_k[st], 16384);
+          tma_load_2d(sK + st * 16384, &tmQKV, &bar_k[st], p.k_col + ld.g * 64, (int)(ld.row_base + (long long)(ld.kv_lo + ld_j) * 128));
+        }
       };
       auto ld_v = [&]() {
         const int st = (int)(ld_g & 1);
-        mbar_expect_tx(&bar_v[st], 16384);
-        tma_load_2d(sV + st * 16384, &tmQKV, &bar_v[st], p.v_col + ld.g * 64, (int)(ld.row_base + (long long)(ld.kv_lo + ld_j) * 128));
+        if (leader) {
+          mbar_expect_tx(&bar_v[st], 16384);
+          tma_load_2d(sV + st * 16384, &tmQKV, &bar_v[st], p.v_col + ld.g * 64, (int)(ld.row_base + (long long)(ld.kv_lo + ld_j) * 128));
+        }
       };
       // base descriptors (scalars, selected by ternaries: indexable arrays would live in local memory)
       const uint64_t dQ00 = umma_desc_sw128(smem_u32(sQ), 0, 1024), dQ01 = umma_desc_sw128(smem_u32(sQ + 16384), 0, 1024);
@@ -171,9 +192,11 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
       auto issue_s = [&](int h, int qbuf, int st) {
 #pragma unroll
         const uint64_t dq = desc_q(qbuf, h), dk = st ? dK1 : dK0;
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem + h * 128, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
-        umma_commit(&bar_s[h]);
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + h * 128, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
+          umma_commit(&bar_s[h]);
+        }
       };
       FwdItem cur = ld;
       load_q(cur, 0);
@@ -198,6 +221,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
           for (int h = 0; h < 2; ++h) {
             mbar_wait(&bar_p[h], ph);                     // P_h(g) in smem, S_h(g) consumed
             tc_fence_after();
+            if (leader) ATTN_EVT(g, h * 2);
             const bool more_here = (j + 1 < cur.n_kv);
             const bool next_s = more_here || nxt_idx >= 0;  // stream tile g+1 exists (maybe the next item's first tile)
             if (h == 0) {
@@ -213,22 +237,27 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
             // dependent integer instructions on ONE thread, was the pace-setter of the whole kernel)
             if (next_s) {
               const uint64_t dq = desc_q((more_here ? n : n + 1) & 1, h), dk = (st ^ 1) ? dK1 : dK0;
+              if (leader) {
 #if !(defined(ATTN_X) && (ATTN_X & 64))  /* timing experiment: no S MMAs in the steady state */
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(tmem + h * 128, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem + h * 128, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
 #endif
-              umma_commit(&bar_s[h]);
+                umma_commit(&bar_s[h]);
+              }
             }
             {
               const uint64_t dp = h ? dP1 : dP0, dv = st ? dV1 : dV0;
+              if (leader) {
 #if !(defined(ATTN_X) && (ATTN_X & 32))  /* timing experiment: no PV MMAs */
 #pragma unroll
-              for (int k = 0; k < 8; ++k)
-                umma_bf16(tmem + 256 + h * 64, dp + (k >> 2) * 1024 + (k & 3) * 2, dv + k * 128, idesc_pv,
-                          (k > 0 || j > 0) ? 1u : 0u);  // O accumulates in TMEM
+                for (int k = 0; k < 8; ++k)
+                  umma_bf16(tmem + 256 + h * 64, dp + (k >> 2) * 1024 + (k & 3) * 2, dv + k * 128, idesc_pv,
+                            (k > 0 || j > 0) ? 1u : 0u);  // O accumulates in TMEM
 #endif
-              umma_commit(&bar_pv[h]);
+                umma_commit(&bar_pv[h]);
+              }
             }
+            if (leader) ATTN_EVT(g, h * 2 + 1);
           }
           if (ld_more()) {  // stream tile g+2 -> stage st: its S MMAs were consumed (bar_p seen); V waits for the PV MMAs
             ld_k();
@@ -237,6 +266,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
             ld_v();
             ld_advance();
           }
+          if (leader) ATTN_EVT(g, 4);
         }
         cur = nxt;
       }
@@ -299,6 +329,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
 #else
           const bool any_need = head_sync_or(hh, !SILU && m_ref == -INFINITY);
 #endif
+          if ((warp & 7) == 0 && lane == 0) ATTN_EVT(g, 5 + hh * 5);
           const bool more_here = (j + 1 < cur.n_kv);
           const bool has_next = more_here || (nxt_idx >= 0);
           if (half == 0 && has_next)  // ids of stream tile g+1: issue the global load early, publish it a phase later
@@ -317,6 +348,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
           }
           mbar_wait(&bar_s[hh], (uint32_t)(g & 1));
           tc_fence_after();
+          if ((warp & 7) == 0 && lane == 0) ATTN_EVT(g, 6 + hh * 5);
           if (any_need) {
             // row max over the run's columns (a superset of the visible ones: any finite reference works)
             float mx = -INFINITY;
@@ -344,6 +376,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
             mbar_wait(&bar_pv[hh], (uint32_t)((g - 1) & 1));
             tc_fence_after();
           }
+          if ((warp & 7) == 0 && lane == 0) ATTN_EVT(g, 7 + hh * 5);
           const float mscaled = (m_ref == -INFINITY) ? 0.f : m_ref * kScaleLog2;
           float lsum = 0.f;
 #if defined(ATTN_X) && (ATTN_X & 8)  /* timing experiment: no exp pass at all */
@@ -398,6 +431,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
 #endif
           }
           l_run += lsum;
+          if ((warp & 7) == 0 && lane == 0) ATTN_EVT(g, 8 + hh * 5);
           if (has_next) publish_ids(g + 1);  // the id load was issued at the top of the tile: its latency hid behind the exp pass
 #if !(defined(ATTN_X) && (ATTN_X & 4))  /* timing experiment 4: no async-proxy fence */
           fence_async_smem();
@@ -405,6 +439,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_p[hh]);  // one arrival per warp: 8 instead of 256 serialised updates of one mbarrier
+          if ((warp & 7) == 0 && lane == 0) ATTN_EVT(g, 9 + hh * 5);
         }
         // the accumulated P.V of the item's tiles, then normalise with the row sum of both halves
         mbar_wait(&bar_pv[hh], (uint32_t)((g - 1) & 1));
@@ -905,3 +940,9 @@ int launch_attn_bwd_pair(const CUtensorMap& tq128, const CUtensorMap& tq64, cons
 }
 
 }  // namespace graft
+
+#ifdef ATTN_TRACE
+extern "C" int graft_debug_attn_trace(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, graft::g_attn_trace, sizeof(long long) * 48 * 16);
+}
+#endif
