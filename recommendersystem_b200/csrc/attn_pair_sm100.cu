@@ -190,7 +190,6 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
       const uint64_t dP0 = umma_desc_sw128(smem_u32(sP), 0, 1024), dP1 = umma_desc_sw128(smem_u32(sP + 32768), 0, 1024);
       auto desc_q = [&](int qbuf, int h) { return qbuf ? (h ? dQ11 : dQ10) : (h ? dQ01 : dQ00); };
       auto issue_s = [&](int h, int qbuf, int st) {
-#pragma unroll
         const uint64_t dq = desc_q(qbuf, h), dk = st ? dK1 : dK0;
         if (leader) {
 #pragma unroll
