@@ -201,6 +201,10 @@ typedef struct {
    * point-wise attention out = sum_s silu(q.k_s/8)/n * v_s over the same visibility, n = tokens of the
    * query's user run (BASELINE configs[2]; the reference has no such code: oracle = oracle/cloze_oracle.py) */
   int mode;
+  /* graft_attn_bwd only, optional: RoPE tables [max_pos, 32] fp32.  When given, dq and dk are written as the
+   * gradient of the un-rotated projections (the transpose rotation of transformer.model.py:182-190 at the
+   * token's row position is applied before the store), so no separate inverse-RoPE pass is needed. */
+  const float* rope_cos; const float* rope_sin;
 } graft_attn_args;
 int graft_attn_fwd(const graft_attn_args* a, void* out_bf16, float* lse, graft_stream_t stream);
 /* dqkv has the layout of qkv; dout [T,H*64] bf16.  delta scratch [H,T] fp32 */

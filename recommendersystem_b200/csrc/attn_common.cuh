@@ -17,6 +17,7 @@ struct AttnDev {
   const float* delta;                        // bwd
   __nv_bfloat16* dqkv; long long ld;         // bwd output (layout of qkv)
   int mode;                                  // 0 softmax, 1 point-wise SiLU (pair kernels only)
+  const float* rope_cos; const float* rope_sin;  // bwd (optional): [max_pos, 32] tables; dq / dk are stored un-rotated
 };
 
 // byte offset of (row, 16-byte chunk) inside a [rows x 128 B] SW128 K-major tile
@@ -63,6 +64,25 @@ __device__ __forceinline__ void store_row_bf16_32(__nv_bfloat16* dst, const floa
     reinterpret_cast<uint4*>(dst)[q8] =
         make_uint4(pack_bf16(v[8 * q8] * mul, v[8 * q8 + 1] * mul), pack_bf16(v[8 * q8 + 2] * mul, v[8 * q8 + 3] * mul),
                    pack_bf16(v[8 * q8 + 4] * mul, v[8 * q8 + 5] * mul), pack_bf16(v[8 * q8 + 6] * mul, v[8 * q8 + 7] * mul));
+}
+
+// backward of RoPE (transformer.model.py:182-190) on 32 consecutive dims (16 pairs: dims 32*half ...) of one head
+// row held in registers: the transpose rotation x0' = x0 c + x1 s, x1' = -x0 s + x1 c at the token's position
+__device__ __forceinline__ void unrope_row_32(float (&v)[32], const AttnDev& p, int pos, int half) {
+  const float4* c4 = reinterpret_cast<const float4*>(p.rope_cos + (long long)pos * 32 + half * 16);
+  const float4* s4 = reinterpret_cast<const float4*>(p.rope_sin + (long long)pos * 32 + half * 16);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 c = __ldg(c4 + q), s = __ldg(s4 + q);
+    const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = 8 * q + 2 * e;
+      const float x0 = v[j], x1 = v[j + 1];
+      v[j] = x0 * cc[e] + x1 * ss[e];
+      v[j + 1] = x1 * cc[e] - x0 * ss[e];
+    }
+  }
 }
 
 // implemented in attn_pair_sm100.cu; used when H/G is even

@@ -662,6 +662,7 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     __nv_bfloat16* drow = p.dqkv + tq * p.ld + h * 64 + half * 32;
     float v[32];
     tmem_ld_32x32_f(t_b + 128 + half * 32, v);
+    if (p.rope_cos) unrope_row_32(v, p, (int)(tq % p.row_len), half);  // d(q before RoPE): transpose rotation, fused here
     store_row_bf16_32(drow, v, 1.f);
   }
   tc_fence_before();
@@ -890,6 +891,7 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
     __nv_bfloat16* drow = p.dqkv + tk * p.ld + (hh == 0 ? p.v_col : p.k_col) + g * 64 + half * 32;
     float v[32];
     tmem_ld_32x32_f(t_acc, v);
+    if (p.rope_cos && hh == 1) unrope_row_32(v, p, (int)(tk % p.row_len), half);  // dK (slot 1) only: V is not rotated
     store_row_bf16_32(drow, v, 1.f);
   }
   tc_fence_before();

@@ -55,6 +55,7 @@ class AttnArgs(C.Structure):
         ("qkv", vp), ("ld", i64), ("k_col", C.c_int), ("v_col", C.c_int),
         ("H", C.c_int), ("G", C.c_int), ("rows", C.c_int), ("row_len", C.c_int),
         ("tm_tok", vp), ("seg_start", vp), ("seg_end", vp), ("mode", C.c_int),
+        ("rope_cos", vp), ("rope_sin", vp),
     ]
 
 
@@ -325,12 +326,14 @@ def check_rows(userid_bs):
 ATTN_SOFTMAX, ATTN_SILU = 0, 1
 
 
-def attn_args(qkv, H, G, rows, row_len, tm_tok, seg_s, seg_e, mode=ATTN_SOFTMAX):
+def attn_args(qkv, H, G, rows, row_len, tm_tok, seg_s, seg_e, mode=ATTN_SOFTMAX, rope=None):
     a = AttnArgs()
     a.qkv, a.ld, a.k_col, a.v_col = vp(qkv.data_ptr()), qkv.shape[1], H * 64, (H + G) * 64
     a.H, a.G, a.rows, a.row_len = H, G, rows, row_len
     a.tm_tok, a.seg_start, a.seg_end = ptr(tm_tok), ptr(seg_s), ptr(seg_e)
     a.mode = mode
+    if rope is not None:  # (cos, sin) tables: the backward stores dq / dk already un-rotated
+        a.rope_cos, a.rope_sin = ptr(rope[0]), ptr(rope[1])
     return a
 
 

@@ -532,9 +532,11 @@ class _ClozeStep(torch.autograd.Function):
                 L.gemm(dh16, ao, g_o, dm, H * 64, T, a_kmajor=False, lda=dm, b_kmajor=False, ldb=H * 64, epilogue=L.EPI_F32,
                        split_k=-1)
             dqkv = _bf16((T, QKV), dev); delta = _f32((H, T), dev)
-            at = L.attn_args(qkv, H, G, B, 2 * S, tm_tok, seg_s, seg_e, mode=_attn_mode(cfg))
+            fused_unrope = (H // G) % 2 == 0  # the pair kernels un-rotate dq / dk in their final store
+            at = L.attn_args(qkv, H, G, B, 2 * S, tm_tok, seg_s, seg_e, mode=_attn_mode(cfg), rope=(cos, sin) if fused_unrope else None)
             L.attn_bwd(at, ao, dao, lse, dqkv, delta)
-            L.rope(dqkv, H + G, 2 * S, cos, sin, inverse=True)
+            if not fused_unrope:
+                L.rope(dqkv, H + G, 2 * S, cos, sin, inverse=True)
             dxn = dhn  # reuse
             if lora is not None:
                 # q = q0 + (A_q xq) B2_q^T with B2 = 2B:  d(A x) = dq . B2,  dB = 2 dq^T (A x),  dA = d(Ax)^T xq

@@ -277,6 +277,32 @@ def attn_reference(qkv, uid, tm, rows, row_len, H, G):
     return o.transpose(1, 2).reshape(T, H * 64), torch.logsumexp(s, -1)  # lse [rows,H,row_len]
 
 
+def test_attention_bwd_fused_unrope():
+    """graft_attn_bwd with RoPE tables stores dq/dk already un-rotated == plain backward followed by the inverse RoPE kernel
+    (the fused path rotates the fp32 accumulators and rounds once, the two-step path rounds twice)."""
+    rows, row_len, H, G = 3, 512, 4, 2
+    uid, tm, qkv = make_attn_case(rows, row_len, H, G, seed=5)
+    T = rows * row_len
+    seg_s, seg_e = L.token_segments(uid)
+    tm_tok = torch.empty(T, dtype=torch.int32, device=DEV); L.interleave_i32(tm.reshape(-1), tm_tok)
+    inv = 1.0 / (500000.0 ** (torch.arange(0, 64, 2).float() / 64))
+    ang = torch.outer(torch.arange(row_len).float(), inv)
+    cos, sin = torch.cos(ang).to(DEV).contiguous(), torch.sin(ang).to(DEV).contiguous()
+    out = torch.empty(T, H * 64, device=DEV, dtype=torch.bfloat16); lse = torch.empty(H, T, device=DEV)
+    a0 = L.attn_args(qkv, H, G, rows, row_len, tm_tok, seg_s, seg_e)
+    L.attn_fwd(a0, out, lse)
+    do = g_randn(T, H * 64, seed=12).bfloat16()
+    ref = torch.empty_like(qkv); delta = torch.empty(H, T, device=DEV)
+    L.attn_bwd(a0, out, do, lse, ref, delta)
+    L.rope(ref, H + G, row_len, cos, sin, inverse=True)
+    got = torch.empty_like(qkv)
+    a1 = L.attn_args(qkv, H, G, rows, row_len, tm_tok, seg_s, seg_e, rope=(cos, sin))
+    L.attn_bwd(a1, out, do, lse, got, delta)
+    report("fused unrope dq", got[:, :H * 64], ref[:, :H * 64], 6e-3)
+    report("fused unrope dk", got[:, H * 64:(H + G) * 64], ref[:, H * 64:(H + G) * 64], 6e-3)
+    assert torch.equal(got[:, (H + G) * 64:], ref[:, (H + G) * 64:])   # dv is not rotated
+
+
 def attn_reference_silu(qkv, uid, tm, rows, row_len, H, G):
     """oracle.silu_pointwise_attention on the fused qkv layout (fp32 autograd reference)."""
     from oracle.cloze_oracle import run_lengths, silu_pointwise_attention, visibility
