@@ -3,6 +3,8 @@
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -q --tb=short -p no:cacheprovider -m gpu -x > gpurun_out/pytest_gpu.log 2>&1
 echo "== pytest -m gpu exit $? : $(tail -n 1 gpurun_out/pytest_gpu.log)"; grep -E "FAILED|Error" gpurun_out/pytest_gpu.log | head
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+echo "== smoke exit $? : $(tail -n 1 gpurun_out/smoke.log)"
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "== bench exit $?"; cat gpurun_out/bench.json; tail -n 3 gpurun_out/bench.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2>> gpurun_out/bench.err
