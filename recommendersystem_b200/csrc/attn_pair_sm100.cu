@@ -18,13 +18,36 @@
 
 namespace graft {
 
-constexpr int PAIR_THREADS = 544;
+constexpr int PAIR_THREADS = 576;  // 16 softmax warps, MMA issue warp (16), TMA load warp (17; backward kernels)
+// ATTN_TS: which kernels keep the bf16 probabilities / score gradients in tensor memory and feed them to
+// tcgen05.mma as the A operand (bit 0 forward P, bit 1 dQ kernel dS, bit 2 dK/dV kernel Pt and dSt) instead of
+// staging them in shared memory: no st.shared / async-proxy fence in the softmax warps, and the accumulate MMAs
+// read only their B operand from shared memory.  Uses TMEM columns 384..511, free in all three kernels.
+#ifndef ATTN_TS
+#define ATTN_TS 7
+#endif
+// ATTN_SA: backward kernels issue the score MMA one key (query) tile ahead into a second TMEM buffer (columns 384..511),
+// so the exp pass of tile j+1 starts without waiting for the tensor pipe; dP stays single-buffered and is issued
+// when dS(j) arrives, hidden behind that exp pass (bit 0 dQ kernel, bit 1 dK/dV kernel).
+#ifndef ATTN_SA
+#define ATTN_SA 0
+#endif
+#if ((ATTN_SA & 1) && (ATTN_TS & 2)) || ((ATTN_SA & 2) && (ATTN_TS & 4))
+#error "ATTN_SA and ATTN_TS use the same TMEM columns in the backward kernels"
+#endif
 __device__ unsigned int g_attn_work[4];  // work-item counters of the persistent kernels (zeroed before each launch)
 #ifdef ATTN_TRACE  /* diagnostic build: CTA 0 timestamps the events of its first 48 stream tiles (tools/attn_trace.py) */
 __device__ long long g_attn_trace[48 * 16];
-#define ATTN_EVT(tile, e) do { if (blockIdx.x == 0 && (tile) < 48) g_attn_trace[(tile) * 16 + (e)] = clock64(); } while (0)
+#define ATTN_EVT_ON(tile, e) do { if (blockIdx.x == 0 && (tile) < 48) g_attn_trace[(tile) * 16 + (e)] = clock64(); } while (0)
 #else
+#define ATTN_EVT_ON(tile, e) do { } while (0)
+#endif
+#if defined(ATTN_TRACE) && ATTN_TRACE == 2   /* 2: trace the dQ kernel instead of the forward kernel */
 #define ATTN_EVT(tile, e) do { } while (0)
+#define ATTN_EVT_DQ(tile, e) ATTN_EVT_ON(tile, e)
+#else
+#define ATTN_EVT(tile, e) ATTN_EVT_ON(tile, e)
+#define ATTN_EVT_DQ(tile, e) do { } while (0)
 #endif
 
 __device__ __forceinline__ void head_sync(int h) { asm volatile("bar.sync %0, 256;" ::"r"(h + 1) : "memory"); }
@@ -124,7 +147,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
       // The whole warp runs this control flow (one elected lane performs the TMA / MMA / barrier side effects):
       // addresses and descriptors are then warp-uniform values the compiler keeps in uniform registers, which
       // tcgen05.mma reads directly - a single divergent thread paid four R2UR moves (~100 clk) per MMA instead.
-      const bool leader = (lane == 0);
+      const bool leader = elect_one();  // elect.sync-derived: ptxas then knows ONE thread issues and emits back-to-back UTCHMMAs
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
       if (leader) {
@@ -250,8 +273,13 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
 #if !(defined(ATTN_X) && (ATTN_X & 32))  /* timing experiment: no PV MMAs */
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
+#if ATTN_TS & 1
+                  umma_bf16_ts(tmem + 256 + h * 64, tmem + 384 + h * 64 + k * 8, dv + k * 128, idesc_pv,
+                               (k > 0 || j > 0) ? 1u : 0u);
+#else
                   umma_bf16(tmem + 256 + h * 64, dp + (k >> 2) * 1024 + (k & 3) * 2, dv + k * 128, idesc_pv,
                             (k > 0 || j > 0) ? 1u : 0u);  // O accumulates in TMEM
+#endif
 #endif
                 umma_commit(&bar_pv[h]);
               }
@@ -270,13 +298,15 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
         cur = nxt;
       }
     }
-  } else {
+  } else if (warp < 16) {
     // -------------------------------------------------- softmax warps ---------
     const int hh = warp >> 3, half = (warp >> 2) & 1, wq = warp & 3;
     const int t = wq * 32 + lane;                       // accumulator row
     const uint32_t t_s = tmem + ((uint32_t)(wq * 32) << 16) + hh * 128 + half * 64;
     const uint32_t t_pv = tmem + ((uint32_t)(wq * 32) << 16) + 256 + hh * 64 + half * 32;
     uint8_t* sPblk = sP + hh * 32768 + half * 16384;     // this half's 64-column K-block of P_h
+    const uint32_t t_p = tmem + ((uint32_t)(wq * 32) << 16) + 384 + hh * 64 + half * 32;  // ATTN_TS: bf16 P_h, 64 columns
+    (void)sPblk; (void)t_p;
     int32_t* sTh = sT + hh * 256;
     uint32_t* sZh = sZ + hh * 8;
     float* sXmine = sX + (hh * 2 + half) * 128;
@@ -424,15 +454,21 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
 #if defined(ATTN_X) && (ATTN_X & 2)  /* timing experiment: no P stores (keeps pk alive through l_run) */
             lsum += __uint_as_float(pk[0] ^ pk[5] ^ pk[10] ^ pk[15]) * 1e-30f;
 #else
+#if ATTN_TS & 1
+            tmem_st_32x16(t_p + c2 * 16, pk);  // keys 32 c2 .. +31 of this half, two per column
+#else
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
               *reinterpret_cast<uint4*>(sPblk + sw128_off(t, c2 * 4 + q4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+#endif
 #endif
           }
           l_run += lsum;
           if ((warp & 7) == 0 && lane == 0) ATTN_EVT(g, 8 + hh * 5);
           if (has_next) publish_ids(g + 1);  // the id load was issued at the top of the tile: its latency hid behind the exp pass
-#if !(defined(ATTN_X) && (ATTN_X & 4))  /* timing experiment 4: no async-proxy fence */
+#if ATTN_TS & 1
+          tmem_st_wait();
+#elif !(defined(ATTN_X) && (ATTN_X & 4))  /* timing experiment 4: no async-proxy fence */
           fence_async_smem();
 #endif
           tc_fence_before();
@@ -469,7 +505,8 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
 // ================================================================ dQ ==========
 // CTA = (128-query tile, head pair); 64-key tiles; a thread owns a row and 32 of the 64 columns.
 // smem per head: Q 16K | dO 16K | dS 16K ; shared: K 2x8K | V 2x8K ; ids ; barriers
-constexpr int DQP_SMEM = 2 * 49152 + 4 * 8192 + 2 * 2 * 64 * 4 + 2 * 2 * 2 * 4 + 256 + 1024;
+constexpr int DQ_KV_STAGES = (ATTN_SA & 1) ? 3 : 2;
+constexpr int DQP_SMEM = 2 * 49152 + 2 * DQ_KV_STAGES * 8192 + 2 * 2 * 64 * 4 + 2 * 2 * 2 * 4 + 256 + 1024;
 
 template <bool SILU>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
@@ -480,16 +517,18 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
   uint8_t* sQ = base;                  // [2][16K]
   uint8_t* sDO = sQ + 32768;           // [2][16K]
   uint8_t* sDS = sDO + 32768;          // [2][16K]
-  uint8_t* sK = sDS + 32768;           // [2 st][8K]
-  uint8_t* sV = sK + 16384;            // [2 st][8K]
-  int32_t* sT = reinterpret_cast<int32_t*>(sV + 16384);  // [2 h][2 st][64]
+  uint8_t* sK = sDS + 32768;           // [stages][8K]
+  uint8_t* sV = sK + DQ_KV_STAGES * 8192;  // [stages][8K]
+  int32_t* sT = reinterpret_cast<int32_t*>(sV + DQ_KV_STAGES * 8192);  // [2 h][2 st][64]
   uint32_t* sZ = reinterpret_cast<uint32_t*>(sT + 256);  // [2 h][2 st][2]
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(sZ + 8);
-  uint64_t* bar_kv = bar_q + 1;   // [2]
-  uint64_t* bar_s = bar_kv + 2;   // [2]
-  uint64_t* bar_p = bar_s + 2;    // [2]
+  uint64_t* bar_kv = bar_q + 1;   // [3]
+  uint64_t* bar_s = bar_kv + 3;   // [2 h][2 buffers] (one per head without ATTN_SA)
+  uint64_t* bar_p = bar_s + 4;    // [2]
   uint64_t* bar_dq = bar_p + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_dq + 2);
+  uint64_t* bar_dp = bar_dq + 2;  // [2] (ATTN_SA)
+  uint64_t* bar_free = bar_dp + 2;  // [3] K/V stage free: both heads' dQ MMAs of the tile it held retired (2 commits)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_free + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nqt = p.row_len >> 7;
@@ -504,9 +543,9 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
 
   if (tid == 512) {
     mbar_init(bar_q, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_kv[i], 1); mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); mbar_init(&bar_dq[i], 1);
-    }
+    for (int i = 0; i < 3; ++i) { mbar_init(&bar_kv[i], 1); mbar_init(&bar_free[i], 2); }
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_s[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_p[i], 8); mbar_init(&bar_dq[i], 1); mbar_init(&bar_dp[i], 1); }
     fence_barrier_init();
     mbar_expect_tx(bar_q, 65536);  // Q and dO tiles: independent of the segment bounds, requested first
     for (int h = 0; h < 2; ++h) {
@@ -525,58 +564,117 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
   const int n_kv = kv_hi - kv_lo;
 
   if (warp == 16) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);
-      for (int s = 0; s < 2 && s < n_kv; ++s) {
-        const int kr = (int)(row_base + (long long)(kv_lo + s) * 64);
-        mbar_expect_tx(&bar_kv[s], 16384);
-        tma_load_2d(sK + s * 8192, &tmQKV64, &bar_kv[s], p.k_col + g * 64, kr);
-        tma_load_2d(sV + s * 8192, &tmQKV64, &bar_kv[s], p.v_col + g * 64, kr);
+    // Issue warp.  The whole warp runs the control flow and one elected lane performs the TMA / MMA / barrier side
+    // effects (and the mbarrier polling): descriptors and TMEM addresses are then warp-uniform values held in uniform
+    // registers, which tcgen05.mma reads directly.  A single divergent thread paid two or three R2UR round trips plus
+    // an election retry loop per MMA: ~110 clk per MMA against the 48 clk the tensor pipe needs (N = 64), which made
+    // this warp - 24 MMAs per key tile - the pace-setter of the kernel (timeline: tools/attn_trace_dq.py).
+    const bool leader = elect_one();  // elect.sync-derived: ptxas then knows ONE thread issues and emits back-to-back UTCHMMAs
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);
+    auto wait_u = [&](uint64_t* bar, uint32_t parity) {
+      if (leader) mbar_wait(bar, parity);
+      __syncwarp();
+    };
+    // base descriptors; k-steps add 2 (32 B, K-major) or 128 (2048 B, MN-major) to the 16-byte-unit address field
+    const uint64_t dQ0 = umma_desc_sw128(smem_u32(sQ), 0, 1024), dQ1 = umma_desc_sw128(smem_u32(sQ + 16384), 0, 1024);
+    const uint64_t dO0 = umma_desc_sw128(smem_u32(sDO), 0, 1024), dO1 = umma_desc_sw128(smem_u32(sDO + 16384), 0, 1024);
+    const uint64_t dS0 = umma_desc_sw128(smem_u32(sDS), 0, 1024), dS1 = umma_desc_sw128(smem_u32(sDS + 16384), 0, 1024);
+    const uint64_t dKa = umma_desc_sw128(smem_u32(sK), 0, 1024), dVa = umma_desc_sw128(smem_u32(sV), 0, 1024);
+    const uint64_t dKt = umma_desc_sw128(smem_u32(sK), 8192, 1024);   // K tile as the MN-major B operand of dQ += dS K
+    (void)dS0; (void)dS1;
+    auto issue_s = [&](int h, int i, uint32_t d, uint64_t* bar) {  // S_h(i) = Q_h K(i)^T
+      const uint64_t dq = h ? dQ1 : dQ0, dk = dKa + (uint64_t)((i % DQ_KV_STAGES) * 512);
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(d, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
+        if (bar) umma_commit(bar);
       }
-      auto issue_s = [&](int h, int st) {  // S_h = Q_h K^T, dP_h = dO_h V^T
-        const uint32_t qa = smem_u32(sQ + h * 16384), da = smem_u32(sDO + h * 16384);
-        const uint32_t ka = smem_u32(sK + st * 8192), va = smem_u32(sV + st * 8192);
+    };
+    auto issue_dp = [&](int h, int i, uint64_t* bar) {  // dP_h(i) = dO_h V(i)^T
+      const uint64_t dd = h ? dO1 : dO0, dv = dVa + (uint64_t)((i % DQ_KV_STAGES) * 512);
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + h * 192 + 64, dd + 2 * k, dv + 2 * k, idesc_s, k > 0);
+        umma_commit(bar);
+      }
+    };
+    auto issue_dq = [&](int h, int j) {  // dQ_h += dS_h(j) K(j)
+      const uint64_t dk = dKt + (uint64_t)((j % DQ_KV_STAGES) * 512);
+      if (leader) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + h * 192, umma_desc_sw128(qa + k * 32, 0, 1024), umma_desc_sw128(ka + k * 32, 0, 1024), idesc_s, k > 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + h * 192 + 64, umma_desc_sw128(da + k * 32, 0, 1024), umma_desc_sw128(va + k * 32, 0, 1024), idesc_s, k > 0);
-        umma_commit(&bar_s[h]);
-      };
-      mbar_wait(bar_q, 0);
-      mbar_wait(&bar_kv[0], 0);
+#if ATTN_TS & 2
+          umma_bf16_ts(tmem + h * 192 + 128, tmem + 384 + h * 32 + k * 8, dk + 128 * k, idesc_dq, (j > 0 || k > 0) ? 1u : 0u);
+#else
+          umma_bf16(tmem + h * 192 + 128, (h ? dS1 : dS0) + 2 * k, dk + 128 * k, idesc_dq, (j > 0 || k > 0) ? 1u : 0u);
+#endif
+        umma_commit(&bar_dq[h]);
+        umma_commit(&bar_free[j % DQ_KV_STAGES]);
+      }
+    };
+    wait_u(bar_q, 0);
+    wait_u(&bar_kv[0], 0);
+    tc_fence_after();
+#if ATTN_SA & 1
+    auto s_col = [&](int h, int i) { return (i & 1) ? tmem + 384 + h * 64 : tmem + h * 192; };
+    issue_s(0, 0, s_col(0, 0), &bar_s[0]); issue_dp(0, 0, &bar_dp[0]);
+    issue_s(1, 0, s_col(1, 0), &bar_s[2]); issue_dp(1, 0, &bar_dp[1]);
+    if (n_kv > 1) {
+      wait_u(&bar_kv[1], 0);
       tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(&bar_p[h], j & 1);  // dS_h(j) in smem; S_h/dP_h(j) consumed
-          tc_fence_after();
-          if (j + 1 < n_kv) {  // next S/dP first: the elementwise warps wait on them, not on dQ
-            if (h == 0) {
-              mbar_wait(&bar_kv[st ^ 1], ((j + 1) >> 1) & 1);
-              tc_fence_after();
-            }
-            issue_s(h, st ^ 1);
+      issue_s(0, 1, s_col(0, 1), &bar_s[1]); issue_s(1, 1, s_col(1, 1), &bar_s[3]);
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      for (int h = 0; h < 2; ++h) {
+        wait_u(&bar_p[h], j & 1);  // dS_h(j) in smem; S_h(j) and dP_h(j) consumed
+        tc_fence_after();
+        if (leader) ATTN_EVT_DQ(j, h * 2);
+        if (j + 1 < n_kv) issue_dp(h, j + 1, &bar_dp[h]);  // first: the head's warps are already in the exp pass of tile j+1
+        issue_dq(h, j);
+        if (leader) ATTN_EVT_DQ(j, h * 2 + 1);
+      }
+      if (j + 2 < n_kv) {  // scores two tiles ahead, into the buffer tile j just left
+        wait_u(&bar_kv[(j + 2) % 3], (uint32_t)(((j + 2) / 3) & 1));
+        tc_fence_after();
+        issue_s(0, j + 2, s_col(0, j), &bar_s[j & 1]); issue_s(1, j + 2, s_col(1, j), &bar_s[2 + (j & 1)]);
+      }
+      if (leader) ATTN_EVT_DQ(j, 4);
+    }
+#else
+    issue_s(0, 0, tmem, nullptr); issue_dp(0, 0, &bar_s[0]);
+    issue_s(1, 0, tmem + 192, nullptr); issue_dp(1, 0, &bar_s[1]);
+    for (int j = 0; j < n_kv; ++j) {
+      for (int h = 0; h < 2; ++h) {
+        wait_u(&bar_p[h], j & 1);  // dS_h(j) in smem; S_h/dP_h(j) consumed
+        tc_fence_after();
+        if (leader) ATTN_EVT_DQ(j, h * 2);
+        if (j + 1 < n_kv) {  // next S/dP first: the elementwise warps wait on them, not on dQ
+          if (h == 0) {
+            wait_u(&bar_kv[(j + 1) % DQ_KV_STAGES], (uint32_t)(((j + 1) / DQ_KV_STAGES) & 1));
+            tc_fence_after();
           }
-          const uint32_t sa = smem_u32(sDS + h * 16384), ka = smem_u32(sK + st * 8192);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + h * 192 + 128, umma_desc_sw128(sa + k * 32, 0, 1024), umma_desc_sw128(ka + k * 2048, 8192, 1024), idesc_dq,
-                      (j > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&bar_dq[h]);
+          issue_s(h, j + 1, tmem + h * 192, nullptr);
+          issue_dp(h, j + 1, &bar_s[h]);   // one commit covers S_h and dP_h
         }
-        if (j + 2 < n_kv) {  // stage st is free once both dQ MMAs of tile j retired
-          mbar_wait(&bar_dq[0], j & 1);
-          mbar_wait(&bar_dq[1], j & 1);
-          const int kr = (int)(row_base + (long long)(kv_lo + j + 2) * 64);
-          mbar_expect_tx(&bar_kv[st], 16384);
-          tma_load_2d(sK + st * 8192, &tmQKV64, &bar_kv[st], p.k_col + g * 64, kr);
-          tma_load_2d(sV + st * 8192, &tmQKV64, &bar_kv[st], p.v_col + g * 64, kr);
-        }
+        issue_dq(h, j);
+        if (leader) ATTN_EVT_DQ(j, h * 2 + 1);
+      }
+      if (leader) ATTN_EVT_DQ(j, 4);
+    }
+#endif
+  } else if (warp == 17) {
+    // Load warp: K/V tiles run up to DQ_KV_STAGES ahead; a stage is refilled as soon as both heads' dQ MMAs of the tile
+    // it held retired.  Kept off the MMA warp on purpose: waiting there for MMA retirement drained the tensor pipe once
+    // per key tile while the next dS sat ready (tools/attn_trace_dq.py: 0.76 us of a 2.1 us step).
+    if (elect_one()) {
+      for (int i = 0; i < n_kv; ++i) {
+        const int sg = i % DQ_KV_STAGES;
+        if (i >= DQ_KV_STAGES) mbar_wait(&bar_free[sg], (uint32_t)((i / DQ_KV_STAGES - 1) & 1));
+        const int kr = (int)(row_base + (long long)(kv_lo + i) * 64);
+        mbar_expect_tx(&bar_kv[sg], 16384);
+        tma_load_2d(sK + sg * 8192, &tmQKV64, &bar_kv[sg], p.k_col + g * 64, kr);
+        tma_load_2d(sV + sg * 8192, &tmQKV64, &bar_kv[sg], p.v_col + g * 64, kr);
       }
     }
   } else {
@@ -591,6 +689,7 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     const float gs_n = kScale / (float)max(qe - qs, 1);  // SILU: dS = dP * silu'(s/8) / (8 n)
     const uint32_t t_b = tmem + ((uint32_t)(wq * 32) << 16) + hh * 192;
     uint8_t* sDSh = sDS + hh * 16384;
+    (void)sDSh;
     int32_t* sTh = sT + hh * 128;
     uint32_t* sZh = sZ + hh * 4;
 
@@ -604,14 +703,57 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
         if (lane == 0) sZh[st * 2 + wq] = z;
       }
       head_sync(hh);
+      if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 5 + hh * 5);
       uint32_t w;
       {
         const uint32_t r = range_word(qs - tile0, qe - tile0, half), z = sZh[st * 2 + half];
         w = (r & z) | ((tmq != 0) ? equal_id_word(r, z, sTh + st * 64 + half * 32, tmq) : 0u);
       }
+#if ATTN_SA & 1
+      // scores of tile j were issued a tile ahead: the exp pass starts at once; dP_h(j) (issued when dS_h(j-1) arrived)
+      // lands meanwhile
+      mbar_wait(&bar_s[hh * 2 + (j & 1)], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 6 + hh * 5);
+      uint32_t pk[16];
+      const bool any_vis = __any_sync(0xffffffffu, w != 0u);
+      float s[32];
+      if (any_vis) {
+        tmem_ld_32x32_f(((j & 1) ? tmem + ((uint32_t)(wq * 32) << 16) + 384 + hh * 64 : t_b) + half * 32, s);
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const uint32_t wb = (w >> (8 * g8)) & 0xffu;
+          const bool clean = __all_sync(0xffffffffu, wb == 0xffu);
+#pragma unroll
+          for (int c = 8 * g8; c < 8 * g8 + 8; ++c) {
+            const float e = SILU ? silu_grad_fast(s[c] * kScale) * gs_n : ex2(fmaf(s[c], kScaleLog2, -lse2));
+            s[c] = (clean || ((w >> c) & 1u)) ? e : 0.f;
+          }
+        }
+      }
+      if ((warp & 7) == 0 && lane == 0) if (hh == 0) ATTN_EVT_DQ(j, 15);   // x0: exp pass done, about to wait for dP
+      mbar_wait(&bar_dp[hh], j & 1);
+      tc_fence_after();
+      if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 7 + hh * 5);
+      if (!any_vis) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) pk[q] = 0u;
+      } else {
+        float dp[32];
+        tmem_ld_32x32_f(t_b + 64 + half * 32, dp);
+#pragma unroll
+        for (int c = 0; c < 32; c += 2)
+          pk[c >> 1] = SILU ? pack_bf16(s[c] * dp[c], s[c + 1] * dp[c + 1])
+                            : pack_bf16(s[c] * fmaf(dp[c], kScale, -dlt_s), s[c + 1] * fmaf(dp[c + 1], kScale, -dlt_s));
+      }
+      if (j > 0) mbar_wait(&bar_dq[hh], (j - 1) & 1);  // dS buffer free
+      if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 8 + hh * 5);
+#else
       mbar_wait(&bar_s[hh], j & 1);
+      if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 6 + hh * 5);
       if (j > 0) mbar_wait(&bar_dq[hh], (j - 1) & 1);  // dS buffer free
       tc_fence_after();
+      if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 7 + hh * 5);
       uint32_t pk[16];
       if (!__any_sync(0xffffffffu, w != 0u)) {
 #pragma unroll
@@ -620,6 +762,7 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
         float s[32], dp[32];
         tmem_ld_32x32_f(t_b + half * 32, s);
         tmem_ld_32x32_f(t_b + 64 + half * 32, dp);
+        if ((warp & 7) == 0 && lane == 0 && hh == 0) ATTN_EVT_DQ(j, 15);   // x0: both tiles in registers
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
           const uint32_t wb = (w >> (8 * g8)) & 0xffu;
@@ -649,13 +792,23 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
           }
         }
       }
+#if !(ATTN_SA & 1)
+      if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 8 + hh * 5);
+#endif
+#endif
+#if ATTN_TS & 2
+      tmem_st_32x16(tmem + ((uint32_t)(wq * 32) << 16) + 384 + hh * 32 + half * 16, pk);
+      tmem_st_wait();
+#else
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4)
         *reinterpret_cast<uint4*>(sDSh + sw128_off(t, half * 4 + q4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
       fence_async_smem();
+#endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_p[hh]);  // one arrival per warp: 8 instead of 256 serialised updates of one mbarrier
+      if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 9 + hh * 5);
     }
     mbar_wait(&bar_dq[hh], (n_kv - 1) & 1);
     tc_fence_after();
@@ -677,7 +830,9 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
 // CTA = (128-key tile, kv head); head slot w walks heads g*hpg + w + 2i and their 64-query tiles;
 // a thread owns a key row and 32 of the tile's 64 query columns.
 // smem: K 16K | V 16K | per slot: Q 2x8K, dO 2x8K, Pt 16K, dSt 16K | per-query scalars | barriers
-constexpr int DKVP_SMEM = 32768 + 2 * 65536 + 2 * 2 * 3 * 64 * 4 + 2 * 2 * 2 * 4 + 256 + 1024;
+constexpr int DKV_Q_STAGES = 3;                                   // Q / dO tile stages per head slot
+constexpr int DKV_SLOT = DKV_Q_STAGES * 16384 + 32768;            // per slot: Q [st][8K] | dO [st][8K] | Pt 16K | dSt 16K
+constexpr int DKVP_SMEM = 32768 + 2 * DKV_SLOT + 2 * 2 * 3 * 64 * 4 + 2 * 2 * 2 * 4 + 256 + 1024;
 
 template <bool SILU>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
@@ -687,14 +842,15 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
   uint8_t* base = smem_align1024(smem_raw);
   uint8_t* sK = base;
   uint8_t* sV = sK + 16384;
-  uint8_t* sW = sV + 16384;  // per slot 64K: Q [2][8K] | dO [2][8K] | Pt 16K | dSt 16K
-  int32_t* sT = reinterpret_cast<int32_t*>(sW + 131072);  // [2 slot][2 st][64]
+  uint8_t* sW = sV + 16384;  // per slot: Q [stages][8K] | dO [stages][8K] | Pt 16K | dSt 16K
+  int32_t* sT = reinterpret_cast<int32_t*>(sW + 2 * DKV_SLOT);  // [2 slot][2 st][64]
   float* sL = reinterpret_cast<float*>(sT + 256);         // [2 slot][2 st][64] lse2
   float* sD = sL + 256;                                    // [2 slot][2 st][64] delta*scale
   uint32_t* sZ = reinterpret_cast<uint32_t*>(sD + 256);   // [2 slot][2 st][2]
   uint64_t* bar_k = reinterpret_cast<uint64_t*>(sZ + 8);
-  uint64_t* bar_q = bar_k + 1;     // [2 slot][2 st]
-  uint64_t* bar_s = bar_q + 4;     // [2]
+  uint64_t* bar_q = bar_k + 1;     // [2 slot][stages] Q / dO tile landed
+  uint64_t* bar_qfree = bar_q + 2 * DKV_Q_STAGES;  // [2 slot][stages] the accumulate MMAs that read the stage retired
+  uint64_t* bar_s = bar_qfree + 2 * DKV_Q_STAGES;  // [2]
   uint64_t* bar_p = bar_s + 2;     // [2]
   uint64_t* bar_acc = bar_p + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 2);
@@ -710,7 +866,7 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
 
   if (tid == 512) {
     mbar_init(bar_k, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&bar_q[i], 1);
+    for (int i = 0; i < 2 * DKV_Q_STAGES; ++i) { mbar_init(&bar_q[i], 1); mbar_init(&bar_qfree[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); mbar_init(&bar_acc[i], 1); }
     fence_barrier_init();
     mbar_expect_tx(bar_k, 32768);  // this CTA's K and V tiles: requested before the sync / segment loads
@@ -729,21 +885,14 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
   const int n_it = n_q * (hpg >> 1);
 
   if (warp == 16) {
-    if (lane == 0) {
+    // MMA issue warp (one elect.sync-chosen thread; see the dQ kernel for why not lane == 0 and why loads live elsewhere)
+    if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 64, 0, 1);
-      auto load_q = [&](int w, int it) {
-        const int st = it & 1;
-        const int h = g * hpg + w + 2 * (it / n_q);
-        const int qr = (int)(row_base + (long long)(q_lo + it % n_q) * 64);
-        uint8_t* wb = sW + w * 65536;
-        mbar_expect_tx(&bar_q[w * 2 + st], 16384);
-        tma_load_2d(wb + st * 8192, &tmQKV64, &bar_q[w * 2 + st], h * 64, qr);
-        tma_load_2d(wb + 16384 + st * 8192, &tmDO64, &bar_q[w * 2 + st], h * 64, qr);
-      };
       auto issue_s = [&](int w, int st) {  // St_w = K Q^T, dPt_w = V dO^T
-        uint8_t* wb = sW + w * 65536;
-        const uint32_t ka = smem_u32(sK), va = smem_u32(sV), qa = smem_u32(wb + st * 8192), da = smem_u32(wb + 16384 + st * 8192);
+        uint8_t* wb = sW + w * DKV_SLOT;
+        const uint32_t ka = smem_u32(sK), va = smem_u32(sV), qa = smem_u32(wb + st * 8192);
+        const uint32_t da = smem_u32(wb + DKV_Q_STAGES * 8192 + st * 8192);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem + w * 128, umma_desc_sw128(ka + k * 32, 0, 1024), umma_desc_sw128(qa + k * 32, 0, 1024), idesc_s, k > 0);
@@ -752,42 +901,64 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
           umma_bf16(tmem + w * 128 + 64, umma_desc_sw128(va + k * 32, 0, 1024), umma_desc_sw128(da + k * 32, 0, 1024), idesc_s, k > 0);
         umma_commit(&bar_s[w]);
       };
-      for (int it = 0; it < 2 && it < n_it; ++it) { load_q(0, it); load_q(1, it); }
       mbar_wait(bar_k, 0);
       for (int w = 0; w < 2; ++w) {
-        mbar_wait(&bar_q[w * 2], 0);
+        mbar_wait(&bar_q[w * DKV_Q_STAGES], 0);
         tc_fence_after();
         issue_s(w, 0);
       }
       for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1;
+        const int st = it % DKV_Q_STAGES, st1 = (it + 1) % DKV_Q_STAGES;
         for (int w = 0; w < 2; ++w) {
           mbar_wait(&bar_p[w], it & 1);  // Pt_w/dSt_w(it) in smem; St_w/dPt_w(it) consumed
           tc_fence_after();
           if (it + 1 < n_it) {  // next St/dPt first: the elementwise warps wait on them
-            mbar_wait(&bar_q[w * 2 + (st ^ 1)], ((it + 1) >> 1) & 1);
+            mbar_wait(&bar_q[w * DKV_Q_STAGES + st1], (uint32_t)(((it + 1) / DKV_Q_STAGES) & 1));
             tc_fence_after();
-            issue_s(w, st ^ 1);
+            issue_s(w, st1);
           }
-          uint8_t* wb = sW + w * 65536;
-          const uint32_t pa = smem_u32(wb + 32768), sa = smem_u32(wb + 49152);
-          const uint32_t qa = smem_u32(wb + st * 8192), da = smem_u32(wb + 16384 + st * 8192);
+          uint8_t* wb = sW + w * DKV_SLOT;
+          const uint32_t pa = smem_u32(wb + DKV_Q_STAGES * 16384), sa = smem_u32(wb + DKV_Q_STAGES * 16384 + 16384);
+          (void)pa; (void)sa;
+          const uint32_t qa = smem_u32(wb + st * 8192), da = smem_u32(wb + DKV_Q_STAGES * 8192 + st * 8192);
           const uint32_t first = (it == 0 && w == 0) ? 0u : 1u;
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // dV += Pt . dO
+#if ATTN_TS & 4
+            umma_bf16_ts(tmem + 256, tmem + 384 + w * 64 + k * 8, umma_desc_sw128(da + k * 2048, 8192, 1024), idesc_acc,
+                         (k > 0) ? 1u : first);
+#else
             umma_bf16(tmem + 256, umma_desc_sw128(pa + k * 32, 0, 1024), umma_desc_sw128(da + k * 2048, 8192, 1024), idesc_acc,
                       (k > 0) ? 1u : first);
+#endif
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // dK += dSt . Q
+#if ATTN_TS & 4
+            umma_bf16_ts(tmem + 320, tmem + 384 + w * 64 + 32 + k * 8, umma_desc_sw128(qa + k * 2048, 8192, 1024), idesc_acc,
+                         (k > 0) ? 1u : first);
+#else
             umma_bf16(tmem + 320, umma_desc_sw128(sa + k * 32, 0, 1024), umma_desc_sw128(qa + k * 2048, 8192, 1024), idesc_acc,
                       (k > 0) ? 1u : first);
+#endif
           umma_commit(&bar_acc[w]);
+          umma_commit(&bar_qfree[w * DKV_Q_STAGES + st]);
         }
-        if (it + 2 < n_it) {
-          for (int w = 0; w < 2; ++w) {
-            mbar_wait(&bar_acc[w], it & 1);  // the accumulate MMAs that read stage st retired
-            load_q(w, it + 2);
-          }
+      }
+    }
+  } else if (warp == 17) {
+    // Load warp: the slots' Q / dO tiles run up to DKV_Q_STAGES iterations ahead of the MMAs
+    if (elect_one()) {
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it % DKV_Q_STAGES;
+        const int qr = (int)(row_base + (long long)(q_lo + it % n_q) * 64);
+        for (int w = 0; w < 2; ++w) {
+          const int h = g * hpg + w + 2 * (it / n_q);
+          uint8_t* wb = sW + w * DKV_SLOT;
+          uint64_t* bar = &bar_q[w * DKV_Q_STAGES + st];
+          if (it >= DKV_Q_STAGES) mbar_wait(&bar_qfree[w * DKV_Q_STAGES + st], (uint32_t)((it / DKV_Q_STAGES - 1) & 1));
+          mbar_expect_tx(bar, 16384);
+          tma_load_2d(wb + st * 8192, &tmQKV64, bar, h * 64, qr);
+          tma_load_2d(wb + DKV_Q_STAGES * 8192 + st * 8192, &tmDO64, bar, h * 64, qr);
         }
       }
     }
@@ -799,9 +970,10 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
     const int ks = p.seg_start[tk], ke = p.seg_end[tk];
     const float inv_n = 1.f / (float)max(ke - ks, 1);  // a key and the queries that see it share one user run
     const uint32_t t_b = tmem + ((uint32_t)(wq * 32) << 16) + hh * 128;
-    uint8_t* wb = sW + hh * 65536;
-    uint8_t* sPT = wb + 32768;
-    uint8_t* sDST = wb + 49152;
+    uint8_t* wb = sW + hh * DKV_SLOT;
+    uint8_t* sPT = wb + DKV_Q_STAGES * 16384;
+    uint8_t* sDST = sPT + 16384;
+    (void)sPT; (void)sDST;
     int32_t* sTh = sT + hh * 128;
     float* sLh = sL + hh * 128;
     float* sDh = sD + hh * 128;
@@ -872,6 +1044,14 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
           }
         }
       }
+#if ATTN_TS & 4
+      {
+        const uint32_t t_a = tmem + ((uint32_t)(wq * 32) << 16) + 384 + hh * 64 + half * 16;
+        tmem_st_32x16(t_a, pp);
+        tmem_st_32x16(t_a + 32, pd);
+        tmem_st_wait();
+      }
+#else
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const uint32_t off = sw128_off(t, half * 4 + q4);
@@ -879,6 +1059,7 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
         *reinterpret_cast<uint4*>(sDST + off) = make_uint4(pd[4 * q4], pd[4 * q4 + 1], pd[4 * q4 + 2], pd[4 * q4 + 3]);
       }
       fence_async_smem();
+#endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_p[hh]);  // one arrival per warp: 8 instead of 256 serialised updates of one mbarrier

@@ -243,7 +243,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  // The two single-thread roles are chosen with elect.sync (not lane == 0): ptxas then knows exactly one thread runs the
+  // role and emits TMA / tcgen05.mma instructions straight from uniform registers; behind a lane compare it wraps every
+  // such instruction in an elect-and-retry loop with R2UR round trips (~100 clk per instruction on the issuing thread).
+  if (warp == 0 && elect_one()) {
     // ------------------------------------------------------ TMA producer ----
     int stage = 0;
     uint32_t phase = 0;
@@ -274,7 +277,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one()) {
     // -------------------------------------------------------- MMA issuer ----
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0;
@@ -456,7 +459,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (sub == 1) {
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (elect_one()) {
               tma_store_2d(&tmC, stg, n0 + (c - 1) * 32, orow0);
               tma_store_commit();
             }
@@ -471,7 +474,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 make_uint4(gate[4 * j], gate[4 * j + 1], gate[4 * j + 2], gate[4 * j + 3]);
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             tma_store_2d(&tmAux, stg, ((n0 + half * (BN / 2)) >> 7) * 64, orow0);
             tma_store_commit();
           }
