@@ -32,6 +32,12 @@ constexpr int PAIR_THREADS = 576;  // 16 softmax warps, MMA issue warp (16), TMA
 #ifndef ATTN_SA
 #define ATTN_SA 0
 #endif
+// ATTN_POLL_ALL: every lane of the MMA issue warp polls the mbarrier (1, default) instead of the elected lane followed
+// by __syncwarp (0).  Measured: the divergent single-lane poll costs the warp ~0.3 us per probe next to the 16 busy
+// softmax warps; all-lane polling: attention fwd 879 -> 801 us, dQ kernel -260 us per C2 layer.
+#ifndef ATTN_POLL_ALL
+#define ATTN_POLL_ALL 1
+#endif
 #if ((ATTN_SA & 1) && (ATTN_TS & 2)) || ((ATTN_SA & 2) && (ATTN_TS & 4))
 #error "ATTN_SA and ATTN_TS use the same TMEM columns in the backward kernels"
 #endif
@@ -42,11 +48,17 @@ __device__ long long g_attn_trace[48 * 16];
 #else
 #define ATTN_EVT_ON(tile, e) do { } while (0)
 #endif
-#if defined(ATTN_TRACE) && ATTN_TRACE == 2   /* 2: trace the dQ kernel instead of the forward kernel */
+#if defined(ATTN_TRACE) && ATTN_TRACE == 3   /* 3: forward kernel, load warp events in slots 5-8, MMA-warp tile waits in 13-15 */
+#define ATTN_EVT(tile, e) do { if ((e) < 5) ATTN_EVT_ON(tile, e); } while (0)
+#define ATTN_EVT_LD(tile, e) ATTN_EVT_ON(tile, e)
+#define ATTN_EVT_DQ(tile, e) do { } while (0)
+#elif defined(ATTN_TRACE) && ATTN_TRACE == 2   /* 2: trace the dQ kernel instead of the forward kernel */
 #define ATTN_EVT(tile, e) do { } while (0)
+#define ATTN_EVT_LD(tile, e) do { } while (0)
 #define ATTN_EVT_DQ(tile, e) ATTN_EVT_ON(tile, e)
 #else
 #define ATTN_EVT(tile, e) ATTN_EVT_ON(tile, e)
+#define ATTN_EVT_LD(tile, e) do { } while (0)
 #define ATTN_EVT_DQ(tile, e) do { } while (0)
 #endif
 
@@ -75,9 +87,15 @@ constexpr float kExpClamp = 120.f;  // log2 units above the row's reference: unr
 // tiles ahead, next item's Q into the other Q buffer) runs across item boundaries: the next item's loads and
 // first S MMA overlap the drain (final O read, normalise, store) of the current one, and barrier init,
 // TMEM allocation and the CTA launch are paid once per SM instead of once per item.
-// smem: Q 2 buf x 2 heads x 16K | K 2x16K | V 2x16K | P 2x32K | mask ids [2 h][2 st][128] | Z [2][2][4] |
-//       row max / row sum exchange [2 h][2 half][128] | barriers
-constexpr int FP_SMEM = 65536 + 32768 + 32768 + 65536 + 2 * 2 * 128 * 4 + 2 * 2 * 4 * 4 + 2 * 2 * 128 * 4 + 256 + 1024;
+// smem: Q 2 buf x 2 heads x 16K | K stages x 16K | V stages x 16K | mask ids [2 h][2 st][128] | Z [2][2][4] |
+//       row max / row sum exchange [2 h][2 half][128] | barriers.  P never touches shared memory: the softmax warps write
+//       it as packed bf16 into TMEM columns 384..511 and the P.V MMAs read it there (A operand from tensor memory).
+// Warp roles: 0-15 softmax; 16 MMA issue (never waits for an MMA to retire); 17 loads: draws work items, publishes
+// them through the ring, and keeps Q (2 buffers) and K/V (FWD_KV_STAGES) filled as the MMAs' commits free them.
+constexpr int FWD_KV_STAGES = 4;
+constexpr int FWD_RING = 8;
+constexpr int FP_SMEM = 65536 + 2 * FWD_KV_STAGES * 16384 + 2 * 2 * 128 * 4 + 2 * 2 * 4 * 4 + 2 * 2 * 128 * 4 + 512 + 1024;
+static_assert(ATTN_TS & 1, "the forward kernel keeps P in tensor memory");
 
 struct FwdItem {
   int qt, h0, g, kv_lo, n_kv;
@@ -107,21 +125,23 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_align1024(smem_raw);
   uint8_t* sQ = base;                 // [2 buffers][2 heads][16K]
-  uint8_t* sK = sQ + 65536;           // [2 stages][16K]
-  uint8_t* sV = sK + 32768;           // [2 stages][16K]
-  uint8_t* sP = sV + 32768;           // [2 heads][32K]
-  int32_t* sT = reinterpret_cast<int32_t*>(sP + 65536);  // [2 h][2 st][128]
+  uint8_t* sK = sQ + 65536;                         // [stages][16K]
+  uint8_t* sV = sK + FWD_KV_STAGES * 16384;          // [stages][16K]
+  int32_t* sT = reinterpret_cast<int32_t*>(sV + FWD_KV_STAGES * 16384);  // [2 h][2 st][128]
   uint32_t* sZ = reinterpret_cast<uint32_t*>(sT + 512);  // [2 h][2 st][4]
   float* sX = reinterpret_cast<float*>(sZ + 16);          // [2 h][2 half][128] partial row max / row sum
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sX + 512);  // [2]
-  uint64_t* bar_k = bar_q + 2;    // [2]
-  uint64_t* bar_v = bar_k + 2;    // [2]
-  uint64_t* bar_s = bar_v + 2;    // [2]
-  uint64_t* bar_p = bar_s + 2;    // [2]
-  uint64_t* bar_pv = bar_p + 2;   // [2]
-  uint64_t* bar_item = bar_pv + 2;  // [4] item ordinal k -> slot k & 3
-  volatile int* sItems = reinterpret_cast<volatile int*>(bar_item + 4);  // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(const_cast<int*>(sItems) + 4);
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sX + 512);  // [2] Q buffer landed
+  uint64_t* bar_k = bar_q + 2;                      // [stages] K tile landed
+  uint64_t* bar_v = bar_k + FWD_KV_STAGES;          // [stages] V tile landed
+  uint64_t* bar_s = bar_v + FWD_KV_STAGES;          // [2]
+  uint64_t* bar_p = bar_s + 2;                      // [2]
+  uint64_t* bar_pv = bar_p + 2;                     // [2]
+  uint64_t* bar_item = bar_pv + 2;                  // [ring] item ordinal k -> slot k & 7
+  uint64_t* bar_kfree = bar_item + FWD_RING;        // [stages] both heads' S MMAs on the stage retired (2 commits)
+  uint64_t* bar_vfree = bar_kfree + FWD_KV_STAGES;  // [stages] both heads' P.V MMAs on the stage retired (2 commits)
+  uint64_t* bar_qfree = bar_vfree + FWD_KV_STAGES;  // [2] both heads' S MMAs of the buffer's item retired (2 commits)
+  volatile int* sItems = reinterpret_cast<volatile int*>(bar_qfree + 2);  // [ring]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(const_cast<int*>(sItems) + FWD_RING);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int first_item = ((int)blockIdx.x < n_items) ? (int)blockIdx.x : -1;
@@ -129,10 +149,13 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
   if (tid == 512) {
     tma_prefetch_desc(&tmQKV);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_q[i], 1); mbar_init(&bar_k[i], 1); mbar_init(&bar_v[i], 1); mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_p[i], 8); mbar_init(&bar_pv[i], 1);
+      mbar_init(&bar_q[i], 1); mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); mbar_init(&bar_pv[i], 1);
+      mbar_init(&bar_qfree[i], 2);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&bar_item[i], 1);
+    for (int i = 0; i < FWD_KV_STAGES; ++i) {
+      mbar_init(&bar_k[i], 1); mbar_init(&bar_v[i], 1); mbar_init(&bar_kfree[i], 2); mbar_init(&bar_vfree[i], 2);
+    }
+    for (int i = 0; i < FWD_RING; ++i) mbar_init(&bar_item[i], 1);
     fence_barrier_init();
   }
   if (warp == 16) tmem_alloc<512>(tmem_slot);
@@ -143,159 +166,130 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
 
   if (warp == 16) {
     if (first_item >= 0) {
-      // ------------------------------------------------ issue warp ------------
-      // The whole warp runs this control flow (one elected lane performs the TMA / MMA / barrier side effects):
-      // addresses and descriptors are then warp-uniform values the compiler keeps in uniform registers, which
-      // tcgen05.mma reads directly - a single divergent thread paid four R2UR moves (~100 clk) per MMA instead.
-      const bool leader = elect_one();  // elect.sync-derived: ptxas then knows ONE thread issues and emits back-to-back UTCHMMAs
+      // ------------------------------------------------ MMA issue warp --------
+      // The whole warp runs this control flow and one elect.sync-chosen lane performs the MMA / barrier side effects and
+      // the mbarrier polling (an elect-derived predicate lets ptxas emit back-to-back UTCHMMAs from uniform registers; a
+      // lane == 0 compare wrapped every MMA in an election retry loop with R2UR round trips, ~100 clk each).  It only
+      // ever waits for data (P from the softmax warps, tiles from the load warp), never for an MMA to retire: stage and
+      // buffer release travels to the load warp through tcgen05.commit.
+      const bool leader = elect_one();
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
-      if (leader) {
-        sItems[0] = first_item;        // ordinal 0 is blockIdx.x (published too, so every ring slot sees one arrival per
-        mbar_arrive(&bar_item[0]);     // ordinal and the waiters' phase is (k >> 2) & 1); ordinals >= 1 come from the counter
-      }
-      int fetched = 1;
-      auto item_of = [&](int k) -> int {  // index of this CTA's k-th item (-1: no more work), drawing it if needed
-        if (k == 0) return first_item;
-        while (fetched <= k) {
-          if (leader) {
-            int idx = (int)gridDim.x + (int)atomicAdd(work_counter, 1u);
-            if (idx >= n_items) idx = -1;
-            sItems[fetched & 3] = idx;
-            mbar_arrive(&bar_item[fetched & 3]);   // release: the softmax warps read the slot after their wait
-          }
-          __syncwarp();
-          ++fetched;
-        }
-        return sItems[k & 3];
+      auto wait_u = [&](uint64_t* bar, uint32_t parity) {
+#if ATTN_POLL_ALL
+        mbar_wait(bar, parity);
+#else
+        if (leader) mbar_wait(bar, parity);
+        __syncwarp();
+#endif
       };
-      auto load_q = [&](const FwdItem& it, int n) {  // item n's two Q tiles -> Q buffer n & 1
-        uint8_t* q = sQ + (n & 1) * 32768;
-        const int q_row = (int)(it.row_base + it.qt * 128);
-        if (leader) {
-          mbar_expect_tx(&bar_q[n & 1], 32768);
-          tma_load_2d(q, &tmQKV, &bar_q[n & 1], it.h0 * 64, q_row);
-          tma_load_2d(q + 16384, &tmQKV, &bar_q[n & 1], (it.h0 + 1) * 64, q_row);
-        }
+      auto item_at = [&](int k) -> int {  // index of this CTA's k-th item (-1: no more work), published by the load warp
+        wait_u(&bar_item[k & (FWD_RING - 1)], (uint32_t)((k / FWD_RING) & 1));
+        return sItems[k & (FWD_RING - 1)];
       };
-      // K/V loads run two stream tiles ahead of the MMAs, through their own item cursor
-      FwdItem ld = fwd_item(p, first_item);
-      int ld_n = 0, ld_j = 0, ld_idx = first_item;
-      long long ld_g = 0;  // stream index of the next tile to load
-      auto ld_more = [&]() { return ld_idx >= 0; };
-      auto ld_advance = [&]() {
-        ++ld_g;
-        if (++ld_j == ld.n_kv) {
-          ld_j = 0;
-          ld_idx = item_of(++ld_n);
-          if (ld_idx >= 0) ld = fwd_item(p, ld_idx);
-        }
-      };
-      auto ld_k = [&]() {
-        const int st = (int)(ld_g & 1);
-        if (leader) {
-          mbar_expect_tx(&bar_k[st], 16384);
-          tma_load_2d(sK + st * 16384, &tmQKV, &bar_k[st], p.k_col + ld.g * 64, (int)(ld.row_base + (long long)(ld.kv_lo + ld_j) * 128));
-        }
-      };
-      auto ld_v = [&]() {
-        const int st = (int)(ld_g & 1);
-        if (leader) {
-          mbar_expect_tx(&bar_v[st], 16384);
-          tma_load_2d(sV + st * 16384, &tmQKV, &bar_v[st], p.v_col + ld.g * 64, (int)(ld.row_base + (long long)(ld.kv_lo + ld_j) * 128));
-        }
-      };
-      // base descriptors (scalars, selected by ternaries: indexable arrays would live in local memory)
+      // base descriptors; stages / k-steps are offsets in the 16-byte-unit address field
       const uint64_t dQ00 = umma_desc_sw128(smem_u32(sQ), 0, 1024), dQ01 = umma_desc_sw128(smem_u32(sQ + 16384), 0, 1024);
       const uint64_t dQ10 = umma_desc_sw128(smem_u32(sQ + 32768), 0, 1024), dQ11 = umma_desc_sw128(smem_u32(sQ + 49152), 0, 1024);
-      const uint64_t dK0 = umma_desc_sw128(smem_u32(sK), 0, 1024), dK1 = umma_desc_sw128(smem_u32(sK + 16384), 0, 1024);
-      const uint64_t dV0 = umma_desc_sw128(smem_u32(sV), 16384, 1024), dV1 = umma_desc_sw128(smem_u32(sV + 16384), 16384, 1024);
-      const uint64_t dP0 = umma_desc_sw128(smem_u32(sP), 0, 1024), dP1 = umma_desc_sw128(smem_u32(sP + 32768), 0, 1024);
+      const uint64_t dKb = umma_desc_sw128(smem_u32(sK), 0, 1024), dVb = umma_desc_sw128(smem_u32(sV), 16384, 1024);
       auto desc_q = [&](int qbuf, int h) { return qbuf ? (h ? dQ11 : dQ10) : (h ? dQ01 : dQ00); };
-      auto issue_s = [&](int h, int qbuf, int st) {
-        const uint64_t dq = desc_q(qbuf, h), dk = st ? dK1 : dK0;
+      auto issue_s = [&](int h, int qbuf, int st, bool last_of_item) {  // S_h = Q_h K^T of one stream tile
+        const uint64_t dq = desc_q(qbuf, h), dk = dKb + (uint64_t)(st * 1024);
         if (leader) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tmem + h * 128, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
           umma_commit(&bar_s[h]);
+          umma_commit(&bar_kfree[st]);
+          if (last_of_item) umma_commit(&bar_qfree[qbuf]);
         }
       };
-      FwdItem cur = ld;
-      load_q(cur, 0);
-      for (int s = 0; s < 2 && ld_more(); ++s) { ld_k(); ld_v(); ld_advance(); }
+      FwdItem cur = fwd_item(p, first_item);
       FwdItem nxt = cur;
-      int nxt_idx = item_of(1);
-      if (nxt_idx >= 0) { nxt = fwd_item(p, nxt_idx); load_q(nxt, 1); }
-      mbar_wait(&bar_q[0], 0);
-      mbar_wait(&bar_k[0], 0);
+      int nxt_idx = item_at(1);
+      if (nxt_idx >= 0) nxt = fwd_item(p, nxt_idx);
+      wait_u(&bar_q[0], 0);
+      wait_u(&bar_k[0], 0);
       tc_fence_after();
-      issue_s(0, 0, 0);
-      issue_s(1, 0, 0);
+      issue_s(0, 0, 0, cur.n_kv == 1);
+      issue_s(1, 0, 0, cur.n_kv == 1);
       long long g = 0;  // stream tile counter
       for (int n = 0, cur_idx = first_item; cur_idx >= 0; ++n, cur_idx = nxt_idx) {
-        if (n >= 1) {  // Q buffer (n+1)&1 held item n-1: all of its S MMAs were consumed
-          nxt_idx = item_of(n + 1);
-          if (nxt_idx >= 0) { nxt = fwd_item(p, nxt_idx); load_q(nxt, n + 1); }
+        if (n >= 1) {
+          nxt_idx = item_at(n + 1);
+          if (nxt_idx >= 0) nxt = fwd_item(p, nxt_idx);
         }
         for (int j = 0; j < cur.n_kv; ++j, ++g) {
-          const int st = (int)(g & 1);
-          const uint32_t ph = (uint32_t)(g & 1);
+          const int st = (int)(g % FWD_KV_STAGES), st1 = (int)((g + 1) % FWD_KV_STAGES);
+          const bool more_here = (j + 1 < cur.n_kv);
+          const bool next_s = more_here || nxt_idx >= 0;  // stream tile g+1 exists (maybe the next item's first tile)
+          // the tiles this step's MMAs read were requested several steps ago: check them off while the warp would
+          // be idle anyway (every mbarrier probe costs this warp ~0.3 us next to 16 busy softmax warps), not between the
+          // arrival of P and the MMAs that wait for it
+          if (next_s) {
+            if (!more_here) wait_u(&bar_q[(n + 1) & 1], (uint32_t)(((n + 1) >> 1) & 1));
+            wait_u(&bar_k[st1], (uint32_t)(((g + 1) / FWD_KV_STAGES) & 1));
+          }
+          wait_u(&bar_v[st], (uint32_t)((g / FWD_KV_STAGES) & 1));
+          if (leader) ATTN_EVT_LD(g, 15);
           for (int h = 0; h < 2; ++h) {
-            mbar_wait(&bar_p[h], ph);                     // P_h(g) in smem, S_h(g) consumed
+            wait_u(&bar_p[h], (uint32_t)(g & 1));         // P_h(g) in TMEM, S_h(g) consumed
             tc_fence_after();
             if (leader) ATTN_EVT(g, h * 2);
-            const bool more_here = (j + 1 < cur.n_kv);
-            const bool next_s = more_here || nxt_idx >= 0;  // stream tile g+1 exists (maybe the next item's first tile)
-            if (h == 0) {
-              if (next_s) {
-                if (!more_here) mbar_wait(&bar_q[(n + 1) & 1], (uint32_t)(((n + 1) >> 1) & 1));
-                mbar_wait(&bar_k[st ^ 1], (uint32_t)(((g + 1) >> 1) & 1));
-              }
-              mbar_wait(&bar_v[st], (uint32_t)((g >> 1) & 1));
-              tc_fence_after();
-            }
-            // Descriptors are loop-invariant up to a 16-byte-unit offset in their low address field: the issue
-            // thread adds constants instead of re-encoding two 64-bit descriptors per MMA (the re-encoding, ~40
-            // dependent integer instructions on ONE thread, was the pace-setter of the whole kernel)
-            if (next_s) {
-              const uint64_t dq = desc_q((more_here ? n : n + 1) & 1, h), dk = (st ^ 1) ? dK1 : dK0;
-              if (leader) {
-#if !(defined(ATTN_X) && (ATTN_X & 64))  /* timing experiment: no S MMAs in the steady state */
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tmem + h * 128, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
-#endif
-                umma_commit(&bar_s[h]);
-              }
-            }
+            if (next_s)  // next S first: the head's softmax warps wait on it, not on P.V
+              issue_s(h, (more_here ? n : n + 1) & 1, st1, more_here ? (j + 2 == cur.n_kv) : (nxt.n_kv == 1));
             {
-              const uint64_t dp = h ? dP1 : dP0, dv = st ? dV1 : dV0;
+              const uint64_t dv = dVb + (uint64_t)(st * 1024);
               if (leader) {
-#if !(defined(ATTN_X) && (ATTN_X & 32))  /* timing experiment: no PV MMAs */
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-#if ATTN_TS & 1
-                  umma_bf16_ts(tmem + 256 + h * 64, tmem + 384 + h * 64 + k * 8, dv + k * 128, idesc_pv,
-                               (k > 0 || j > 0) ? 1u : 0u);
-#else
-                  umma_bf16(tmem + 256 + h * 64, dp + (k >> 2) * 1024 + (k & 3) * 2, dv + k * 128, idesc_pv,
-                            (k > 0 || j > 0) ? 1u : 0u);  // O accumulates in TMEM
-#endif
-#endif
+                for (int k = 0; k < 8; ++k)  // O_h += P_h V: A from TMEM, accumulates across the item's tiles
+                  umma_bf16_ts(tmem + 256 + h * 64, tmem + 384 + h * 64 + k * 8, dv + k * 128, idesc_pv, (k > 0 || j > 0) ? 1u : 0u);
                 umma_commit(&bar_pv[h]);
+                umma_commit(&bar_vfree[st]);
               }
             }
             if (leader) ATTN_EVT(g, h * 2 + 1);
           }
-          if (ld_more()) {  // stream tile g+2 -> stage st: its S MMAs were consumed (bar_p seen); V waits for the PV MMAs
-            ld_k();
-            mbar_wait(&bar_pv[0], ph);
-            mbar_wait(&bar_pv[1], ph);
-            ld_v();
-            ld_advance();
-          }
           if (leader) ATTN_EVT(g, 4);
         }
         cur = nxt;
+      }
+    }
+  } else if (warp == 17) {
+    // ---------------------------------------------------- load warp -----------
+    if (first_item >= 0 && elect_one()) {
+      long long G = 0;  // stream tile counter of the loads
+      int idx = first_item;
+      sItems[0] = first_item;        // ordinal 0 is blockIdx.x (published too, so every ring slot sees one arrival per
+      mbar_arrive(&bar_item[0]);     // ordinal and the waiters' phase is (k / ring) & 1); ordinals >= 1 come from the counter
+      for (int n = 0; idx >= 0; ++n) {
+        const FwdItem it = fwd_item(p, idx);
+        int nidx = (int)gridDim.x + (int)atomicAdd(work_counter, 1u);   // next ordinal: drawn and published a whole item early
+        if (nidx >= n_items) nidx = -1;
+        sItems[(n + 1) & (FWD_RING - 1)] = nidx;
+        mbar_arrive(&bar_item[(n + 1) & (FWD_RING - 1)]);   // release: consumers read the slot after their wait
+        if (n >= 2) mbar_wait(&bar_qfree[n & 1], (uint32_t)(((n >> 1) - 1) & 1));  // item n-2's S MMAs retired
+        {
+          uint8_t* q = sQ + (n & 1) * 32768;
+          const int q_row = (int)(it.row_base + it.qt * 128);
+          mbar_expect_tx(&bar_q[n & 1], 32768);
+          tma_load_2d(q, &tmQKV, &bar_q[n & 1], it.h0 * 64, q_row);
+          tma_load_2d(q + 16384, &tmQKV, &bar_q[n & 1], (it.h0 + 1) * 64, q_row);
+        }
+        for (int j = 0; j < it.n_kv; ++j, ++G) {
+          const int sg = (int)(G % FWD_KV_STAGES);
+          const uint32_t par = (uint32_t)((G / FWD_KV_STAGES - 1) & 1);
+          const int row = (int)(it.row_base + (long long)(it.kv_lo + j) * 128);
+          ATTN_EVT_LD(G, 5);
+          if (G >= FWD_KV_STAGES) mbar_wait(&bar_kfree[sg], par);
+          ATTN_EVT_LD(G, 6);
+          mbar_expect_tx(&bar_k[sg], 16384);
+          tma_load_2d(sK + sg * 16384, &tmQKV, &bar_k[sg], p.k_col + it.g * 64, row);
+          if (G >= FWD_KV_STAGES) mbar_wait(&bar_vfree[sg], par);
+          ATTN_EVT_LD(G, 7);
+          mbar_expect_tx(&bar_v[sg], 16384);
+          tma_load_2d(sV + sg * 16384, &tmQKV, &bar_v[sg], p.v_col + it.g * 64, row);
+          ATTN_EVT_LD(G, 8);
+        }
+        idx = nidx;
       }
     }
   } else if (warp < 16) {
@@ -304,9 +298,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
     const int t = wq * 32 + lane;                       // accumulator row
     const uint32_t t_s = tmem + ((uint32_t)(wq * 32) << 16) + hh * 128 + half * 64;
     const uint32_t t_pv = tmem + ((uint32_t)(wq * 32) << 16) + 256 + hh * 64 + half * 32;
-    uint8_t* sPblk = sP + hh * 32768 + half * 16384;     // this half's 64-column K-block of P_h
-    const uint32_t t_p = tmem + ((uint32_t)(wq * 32) << 16) + 384 + hh * 64 + half * 32;  // ATTN_TS: bf16 P_h, 64 columns
-    (void)sPblk; (void)t_p;
+    const uint32_t t_p = tmem + ((uint32_t)(wq * 32) << 16) + 384 + hh * 64 + half * 32;  // bf16 P_h: 64 columns, this half's 32
     int32_t* sTh = sT + hh * 256;
     uint32_t* sZh = sZ + hh * 8;
     float* sXmine = sX + (hh * 2 + half) * 128;
@@ -336,8 +328,8 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
       long long g = 0;
       for (int n = 0;; ++n) {
         // next item's index (drawn by the issue thread), geometry and row state: requested now, used a whole item later
-        mbar_wait(&bar_item[(n + 1) & 3], (uint32_t)(((n + 1) >> 2) & 1));
-        const int nxt_idx = sItems[(n + 1) & 3];
+        mbar_wait(&bar_item[(n + 1) & (FWD_RING - 1)], (uint32_t)(((n + 1) / FWD_RING) & 1));
+        const int nxt_idx = sItems[(n + 1) & (FWD_RING - 1)];
         FwdItem nxt = cur;
         long long tq_n = tq;
         int tmq_n = 0, qs_n = 0, qe_n = 0;
@@ -454,23 +446,13 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
 #if defined(ATTN_X) && (ATTN_X & 2)  /* timing experiment: no P stores (keeps pk alive through l_run) */
             lsum += __uint_as_float(pk[0] ^ pk[5] ^ pk[10] ^ pk[15]) * 1e-30f;
 #else
-#if ATTN_TS & 1
             tmem_st_32x16(t_p + c2 * 16, pk);  // keys 32 c2 .. +31 of this half, two per column
-#else
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4)
-              *reinterpret_cast<uint4*>(sPblk + sw128_off(t, c2 * 4 + q4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-#endif
 #endif
           }
           l_run += lsum;
           if ((warp & 7) == 0 && lane == 0) ATTN_EVT(g, 8 + hh * 5);
           if (has_next) publish_ids(g + 1);  // the id load was issued at the top of the tile: its latency hid behind the exp pass
-#if ATTN_TS & 1
           tmem_st_wait();
-#elif !(defined(ATTN_X) && (ATTN_X & 4))  /* timing experiment 4: no async-proxy fence */
-          fence_async_smem();
-#endif
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_p[hh]);  // one arrival per warp: 8 instead of 256 serialised updates of one mbarrier
@@ -573,8 +555,12 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
     constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);
     auto wait_u = [&](uint64_t* bar, uint32_t parity) {
+#if ATTN_POLL_ALL
+      mbar_wait(bar, parity);
+#else
       if (leader) mbar_wait(bar, parity);
       __syncwarp();
+#endif
     };
     // base descriptors; k-steps add 2 (32 B, K-major) or 128 (2048 B, MN-major) to the 16-byte-unit address field
     const uint64_t dQ0 = umma_desc_sw128(smem_u32(sQ), 0, 1024), dQ1 = umma_desc_sw128(smem_u32(sQ + 16384), 0, 1024);
@@ -645,15 +631,13 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     issue_s(0, 0, tmem, nullptr); issue_dp(0, 0, &bar_s[0]);
     issue_s(1, 0, tmem + 192, nullptr); issue_dp(1, 0, &bar_s[1]);
     for (int j = 0; j < n_kv; ++j) {
+      // tile j+1 was requested stages ago: check it off before (not after) waiting for dS
+      if (j + 1 < n_kv) wait_u(&bar_kv[(j + 1) % DQ_KV_STAGES], (uint32_t)(((j + 1) / DQ_KV_STAGES) & 1));
       for (int h = 0; h < 2; ++h) {
         wait_u(&bar_p[h], j & 1);  // dS_h(j) in smem; S_h/dP_h(j) consumed
         tc_fence_after();
         if (leader) ATTN_EVT_DQ(j, h * 2);
         if (j + 1 < n_kv) {  // next S/dP first: the elementwise warps wait on them, not on dQ
-          if (h == 0) {
-            wait_u(&bar_kv[(j + 1) % DQ_KV_STAGES], (uint32_t)(((j + 1) / DQ_KV_STAGES) & 1));
-            tc_fence_after();
-          }
           issue_s(h, j + 1, tmem + h * 192, nullptr);
           issue_dp(h, j + 1, &bar_s[h]);   // one commit covers S_h and dP_h
         }
@@ -885,60 +869,70 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
   const int n_it = n_q * (hpg >> 1);
 
   if (warp == 16) {
-    // MMA issue warp (one elect.sync-chosen thread; see the dQ kernel for why not lane == 0 and why loads live elsewhere)
-    if (elect_one()) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 64, 0, 1);
-      auto issue_s = [&](int w, int st) {  // St_w = K Q^T, dPt_w = V dO^T
-        uint8_t* wb = sW + w * DKV_SLOT;
-        const uint32_t ka = smem_u32(sK), va = smem_u32(sV), qa = smem_u32(wb + st * 8192);
-        const uint32_t da = smem_u32(wb + DKV_Q_STAGES * 8192 + st * 8192);
+    // MMA issue warp: warp-uniform control flow, all lanes poll, one elect.sync-chosen lane issues (see the dQ kernel)
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 64, 0, 1);
+    auto wait_u = [&](uint64_t* bar, uint32_t parity) {
+#if ATTN_POLL_ALL
+      mbar_wait(bar, parity);
+#else
+      if (leader) mbar_wait(bar, parity);
+      __syncwarp();
+#endif
+    };
+    const uint64_t dKa = umma_desc_sw128(smem_u32(sK), 0, 1024), dVa = umma_desc_sw128(smem_u32(sV), 0, 1024);
+    auto issue_s = [&](int w, int st) {  // St_w = K Q^T, dPt_w = V dO^T
+      uint8_t* wb = sW + w * DKV_SLOT;
+      const uint64_t dq = umma_desc_sw128(smem_u32(wb + st * 8192), 0, 1024);
+      const uint64_t dd = umma_desc_sw128(smem_u32(wb + DKV_Q_STAGES * 8192 + st * 8192), 0, 1024);
+      if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + w * 128, umma_desc_sw128(ka + k * 32, 0, 1024), umma_desc_sw128(qa + k * 32, 0, 1024), idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + w * 128, dKa + 2 * k, dq + 2 * k, idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + w * 128 + 64, umma_desc_sw128(va + k * 32, 0, 1024), umma_desc_sw128(da + k * 32, 0, 1024), idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + w * 128 + 64, dVa + 2 * k, dd + 2 * k, idesc_s, k > 0);
         umma_commit(&bar_s[w]);
-      };
-      mbar_wait(bar_k, 0);
-      for (int w = 0; w < 2; ++w) {
-        mbar_wait(&bar_q[w * DKV_Q_STAGES], 0);
-        tc_fence_after();
-        issue_s(w, 0);
       }
-      for (int it = 0; it < n_it; ++it) {
-        const int st = it % DKV_Q_STAGES, st1 = (it + 1) % DKV_Q_STAGES;
-        for (int w = 0; w < 2; ++w) {
-          mbar_wait(&bar_p[w], it & 1);  // Pt_w/dSt_w(it) in smem; St_w/dPt_w(it) consumed
-          tc_fence_after();
-          if (it + 1 < n_it) {  // next St/dPt first: the elementwise warps wait on them
-            mbar_wait(&bar_q[w * DKV_Q_STAGES + st1], (uint32_t)(((it + 1) / DKV_Q_STAGES) & 1));
-            tc_fence_after();
-            issue_s(w, st1);
-          }
-          uint8_t* wb = sW + w * DKV_SLOT;
-          const uint32_t pa = smem_u32(wb + DKV_Q_STAGES * 16384), sa = smem_u32(wb + DKV_Q_STAGES * 16384 + 16384);
-          (void)pa; (void)sa;
-          const uint32_t qa = smem_u32(wb + st * 8192), da = smem_u32(wb + DKV_Q_STAGES * 8192 + st * 8192);
-          const uint32_t first = (it == 0 && w == 0) ? 0u : 1u;
+    };
+    wait_u(bar_k, 0);
+    for (int w = 0; w < 2; ++w) {
+      wait_u(&bar_q[w * DKV_Q_STAGES], 0);
+      tc_fence_after();
+      issue_s(w, 0);
+    }
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it % DKV_Q_STAGES, st1 = (it + 1) % DKV_Q_STAGES;
+      if (it + 1 < n_it) {  // the next Q / dO tiles were requested stages ago: check them off before waiting for Pt
+        wait_u(&bar_q[st1], (uint32_t)(((it + 1) / DKV_Q_STAGES) & 1));
+        wait_u(&bar_q[DKV_Q_STAGES + st1], (uint32_t)(((it + 1) / DKV_Q_STAGES) & 1));
+      }
+      for (int w = 0; w < 2; ++w) {
+        wait_u(&bar_p[w], it & 1);  // Pt_w/dSt_w(it) written; St_w/dPt_w(it) consumed
+        tc_fence_after();
+        if (it + 1 < n_it) issue_s(w, st1);  // next St/dPt first: the elementwise warps wait on them
+        uint8_t* wb = sW + w * DKV_SLOT;
+        // dO / Q tiles as MN-major B operands of the accumulate MMAs (k-step = 16 query rows = 2048 B = 128 units)
+        const uint64_t dq_t = umma_desc_sw128(smem_u32(wb + st * 8192), 8192, 1024);
+        const uint64_t dd_t = umma_desc_sw128(smem_u32(wb + DKV_Q_STAGES * 8192 + st * 8192), 8192, 1024);
+#if !(ATTN_TS & 4)
+        const uint64_t dp = umma_desc_sw128(smem_u32(wb + DKV_Q_STAGES * 16384), 0, 1024);
+        const uint64_t ds = umma_desc_sw128(smem_u32(wb + DKV_Q_STAGES * 16384 + 16384), 0, 1024);
+#endif
+        const uint32_t first = (it == 0 && w == 0) ? 0u : 1u;
+        if (leader) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // dV += Pt . dO
 #if ATTN_TS & 4
-            umma_bf16_ts(tmem + 256, tmem + 384 + w * 64 + k * 8, umma_desc_sw128(da + k * 2048, 8192, 1024), idesc_acc,
-                         (k > 0) ? 1u : first);
+            umma_bf16_ts(tmem + 256, tmem + 384 + w * 64 + k * 8, dd_t + 128 * k, idesc_acc, (k > 0) ? 1u : first);
 #else
-            umma_bf16(tmem + 256, umma_desc_sw128(pa + k * 32, 0, 1024), umma_desc_sw128(da + k * 2048, 8192, 1024), idesc_acc,
-                      (k > 0) ? 1u : first);
+            umma_bf16(tmem + 256, dp + 2 * k, dd_t + 128 * k, idesc_acc, (k > 0) ? 1u : first);
 #endif
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // dK += dSt . Q
 #if ATTN_TS & 4
-            umma_bf16_ts(tmem + 320, tmem + 384 + w * 64 + 32 + k * 8, umma_desc_sw128(qa + k * 2048, 8192, 1024), idesc_acc,
-                         (k > 0) ? 1u : first);
+            umma_bf16_ts(tmem + 320, tmem + 384 + w * 64 + 32 + k * 8, dq_t + 128 * k, idesc_acc, (k > 0) ? 1u : first);
 #else
-            umma_bf16(tmem + 320, umma_desc_sw128(sa + k * 32, 0, 1024), umma_desc_sw128(qa + k * 2048, 8192, 1024), idesc_acc,
-                      (k > 0) ? 1u : first);
+            umma_bf16(tmem + 320, ds + 2 * k, dq_t + 128 * k, idesc_acc, (k > 0) ? 1u : first);
 #endif
           umma_commit(&bar_acc[w]);
           umma_commit(&bar_qfree[w * DKV_Q_STAGES + st]);
