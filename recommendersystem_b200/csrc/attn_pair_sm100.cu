@@ -26,20 +26,19 @@ constexpr int PAIR_THREADS = 576;  // 16 softmax warps, MMA issue warp (16), TMA
 #ifndef ATTN_TS
 #define ATTN_TS 7
 #endif
-// ATTN_SA: backward kernels issue the score MMA one key (query) tile ahead into a second TMEM buffer (columns 384..511),
-// so the exp pass of tile j+1 starts without waiting for the tensor pipe; dP stays single-buffered and is issued
-// when dS(j) arrives, hidden behind that exp pass (bit 0 dQ kernel, bit 1 dK/dV kernel).
-#ifndef ATTN_SA
-#define ATTN_SA 0
-#endif
 // ATTN_POLL_ALL: every lane of the MMA issue warp polls the mbarrier (1, default) instead of the elected lane followed
 // by __syncwarp (0).  Measured: the divergent single-lane poll costs the warp ~0.3 us per probe next to the 16 busy
 // softmax warps; all-lane polling: attention fwd 879 -> 801 us, dQ kernel -260 us per C2 layer.
 #ifndef ATTN_POLL_ALL
 #define ATTN_POLL_ALL 1
 #endif
-#if ((ATTN_SA & 1) && (ATTN_TS & 2)) || ((ATTN_SA & 2) && (ATTN_TS & 4))
-#error "ATTN_SA and ATTN_TS use the same TMEM columns in the backward kernels"
+// ATTN_STAGGER_F / _B: ns by which the MMA warp delays the second head's first score MMA (forward / backward kernels), so
+// that the two heads' exp passes (which share the SM's 16 MUFU lanes) alternate instead of running on top of each other
+#ifndef ATTN_STAGGER_F
+#define ATTN_STAGGER_F 0
+#endif
+#ifndef ATTN_STAGGER_B
+#define ATTN_STAGGER_B 0
 #endif
 __device__ unsigned int g_attn_work[4];  // work-item counters of the persistent kernels (zeroed before each launch)
 #ifdef ATTN_TRACE  /* diagnostic build: CTA 0 timestamps the events of its first 48 stream tiles (tools/attn_trace.py) */
@@ -210,6 +209,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
       wait_u(&bar_k[0], 0);
       tc_fence_after();
       issue_s(0, 0, 0, cur.n_kv == 1);
+      if (ATTN_STAGGER_F > 0) __nanosleep(ATTN_STAGGER_F);
       issue_s(1, 0, 0, cur.n_kv == 1);
       long long g = 0;  // stream tile counter
       for (int n = 0, cur_idx = first_item; cur_idx >= 0; ++n, cur_idx = nxt_idx) {
@@ -487,7 +487,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
 // ================================================================ dQ ==========
 // CTA = (128-query tile, head pair); 64-key tiles; a thread owns a row and 32 of the 64 columns.
 // smem per head: Q 16K | dO 16K | dS 16K ; shared: K 2x8K | V 2x8K ; ids ; barriers
-constexpr int DQ_KV_STAGES = (ATTN_SA & 1) ? 3 : 2;
+constexpr int DQ_KV_STAGES = 3;
 constexpr int DQP_SMEM = 2 * 49152 + 2 * DQ_KV_STAGES * 8192 + 2 * 2 * 64 * 4 + 2 * 2 * 2 * 4 + 256 + 1024;
 
 template <bool SILU>
@@ -505,10 +505,10 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
   uint32_t* sZ = reinterpret_cast<uint32_t*>(sT + 256);  // [2 h][2 st][2]
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(sZ + 8);
   uint64_t* bar_kv = bar_q + 1;   // [3]
-  uint64_t* bar_s = bar_kv + 3;   // [2 h][2 buffers] (one per head without ATTN_SA)
+  uint64_t* bar_s = bar_kv + 3;   // [2] (+2 unused)
   uint64_t* bar_p = bar_s + 4;    // [2]
   uint64_t* bar_dq = bar_p + 2;   // [2]
-  uint64_t* bar_dp = bar_dq + 2;  // [2] (ATTN_SA)
+  uint64_t* bar_dp = bar_dq + 2;  // [2] unused
   uint64_t* bar_free = bar_dp + 2;  // [3] K/V stage free: both heads' dQ MMAs of the tile it held retired (2 commits)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_free + 3);
 
@@ -602,33 +602,8 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     wait_u(bar_q, 0);
     wait_u(&bar_kv[0], 0);
     tc_fence_after();
-#if ATTN_SA & 1
-    auto s_col = [&](int h, int i) { return (i & 1) ? tmem + 384 + h * 64 : tmem + h * 192; };
-    issue_s(0, 0, s_col(0, 0), &bar_s[0]); issue_dp(0, 0, &bar_dp[0]);
-    issue_s(1, 0, s_col(1, 0), &bar_s[2]); issue_dp(1, 0, &bar_dp[1]);
-    if (n_kv > 1) {
-      wait_u(&bar_kv[1], 0);
-      tc_fence_after();
-      issue_s(0, 1, s_col(0, 1), &bar_s[1]); issue_s(1, 1, s_col(1, 1), &bar_s[3]);
-    }
-    for (int j = 0; j < n_kv; ++j) {
-      for (int h = 0; h < 2; ++h) {
-        wait_u(&bar_p[h], j & 1);  // dS_h(j) in smem; S_h(j) and dP_h(j) consumed
-        tc_fence_after();
-        if (leader) ATTN_EVT_DQ(j, h * 2);
-        if (j + 1 < n_kv) issue_dp(h, j + 1, &bar_dp[h]);  // first: the head's warps are already in the exp pass of tile j+1
-        issue_dq(h, j);
-        if (leader) ATTN_EVT_DQ(j, h * 2 + 1);
-      }
-      if (j + 2 < n_kv) {  // scores two tiles ahead, into the buffer tile j just left
-        wait_u(&bar_kv[(j + 2) % 3], (uint32_t)(((j + 2) / 3) & 1));
-        tc_fence_after();
-        issue_s(0, j + 2, s_col(0, j), &bar_s[j & 1]); issue_s(1, j + 2, s_col(1, j), &bar_s[2 + (j & 1)]);
-      }
-      if (leader) ATTN_EVT_DQ(j, 4);
-    }
-#else
     issue_s(0, 0, tmem, nullptr); issue_dp(0, 0, &bar_s[0]);
+    if (ATTN_STAGGER_B > 0) __nanosleep(ATTN_STAGGER_B);
     issue_s(1, 0, tmem + 192, nullptr); issue_dp(1, 0, &bar_s[1]);
     for (int j = 0; j < n_kv; ++j) {
       // tile j+1 was requested stages ago: check it off before (not after) waiting for dS
@@ -646,7 +621,6 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
       }
       if (leader) ATTN_EVT_DQ(j, 4);
     }
-#endif
   } else if (warp == 17) {
     // Load warp: K/V tiles run up to DQ_KV_STAGES ahead; a stage is refilled as soon as both heads' dQ MMAs of the tile
     // it held retired.  Kept off the MMA warp on purpose: waiting there for MMA retirement drained the tensor pipe once
@@ -693,46 +667,6 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
         const uint32_t r = range_word(qs - tile0, qe - tile0, half), z = sZh[st * 2 + half];
         w = (r & z) | ((tmq != 0) ? equal_id_word(r, z, sTh + st * 64 + half * 32, tmq) : 0u);
       }
-#if ATTN_SA & 1
-      // scores of tile j were issued a tile ahead: the exp pass starts at once; dP_h(j) (issued when dS_h(j-1) arrived)
-      // lands meanwhile
-      mbar_wait(&bar_s[hh * 2 + (j & 1)], (uint32_t)((j >> 1) & 1));
-      tc_fence_after();
-      if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 6 + hh * 5);
-      uint32_t pk[16];
-      const bool any_vis = __any_sync(0xffffffffu, w != 0u);
-      float s[32];
-      if (any_vis) {
-        tmem_ld_32x32_f(((j & 1) ? tmem + ((uint32_t)(wq * 32) << 16) + 384 + hh * 64 : t_b) + half * 32, s);
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          const uint32_t wb = (w >> (8 * g8)) & 0xffu;
-          const bool clean = __all_sync(0xffffffffu, wb == 0xffu);
-#pragma unroll
-          for (int c = 8 * g8; c < 8 * g8 + 8; ++c) {
-            const float e = SILU ? silu_grad_fast(s[c] * kScale) * gs_n : ex2(fmaf(s[c], kScaleLog2, -lse2));
-            s[c] = (clean || ((w >> c) & 1u)) ? e : 0.f;
-          }
-        }
-      }
-      if ((warp & 7) == 0 && lane == 0) if (hh == 0) ATTN_EVT_DQ(j, 15);   // x0: exp pass done, about to wait for dP
-      mbar_wait(&bar_dp[hh], j & 1);
-      tc_fence_after();
-      if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 7 + hh * 5);
-      if (!any_vis) {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) pk[q] = 0u;
-      } else {
-        float dp[32];
-        tmem_ld_32x32_f(t_b + 64 + half * 32, dp);
-#pragma unroll
-        for (int c = 0; c < 32; c += 2)
-          pk[c >> 1] = SILU ? pack_bf16(s[c] * dp[c], s[c + 1] * dp[c + 1])
-                            : pack_bf16(s[c] * fmaf(dp[c], kScale, -dlt_s), s[c + 1] * fmaf(dp[c + 1], kScale, -dlt_s));
-      }
-      if (j > 0) mbar_wait(&bar_dq[hh], (j - 1) & 1);  // dS buffer free
-      if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 8 + hh * 5);
-#else
       mbar_wait(&bar_s[hh], j & 1);
       if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 6 + hh * 5);
       if (j > 0) mbar_wait(&bar_dq[hh], (j - 1) & 1);  // dS buffer free
@@ -776,10 +710,7 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
           }
         }
       }
-#if !(ATTN_SA & 1)
       if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 8 + hh * 5);
-#endif
-#endif
 #if ATTN_TS & 2
       tmem_st_32x16(tmem + ((uint32_t)(wq * 32) << 16) + 384 + hh * 32 + half * 16, pk);
       tmem_st_wait();
@@ -898,6 +829,7 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
     for (int w = 0; w < 2; ++w) {
       wait_u(&bar_q[w * DKV_Q_STAGES], 0);
       tc_fence_after();
+      if (w == 1 && ATTN_STAGGER_B > 0) __nanosleep(ATTN_STAGGER_B);
       issue_s(w, 0);
     }
     for (int it = 0; it < n_it; ++it) {
