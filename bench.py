@@ -222,8 +222,21 @@ def gpu_bench(args):
     out = None
     if rank == 0:
         pk = peaks()
-        flops = sum(f for _, _, f in gemm_ev)
-        gms = sum(a.elapsed_time(b) for a, b, _ in gemm_ev)
+        flops = sum(e[2] for e in gemm_ev)
+        gms = sum(e[0].elapsed_time(e[1]) for e in gemm_ev)
+        if args.gemm_table:  # per-shape breakdown of the GEMM family (M is the launch's row capacity: masked-row GEMMs do less)
+            agg = {}
+            for e0, e1, f, tag in gemm_ev:
+                a = agg.setdefault(tag, [0, 0.0, 0.0])
+                a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += f
+            EPI = ["bf16", "f32", "f32+=", "resid", "bias", "bias_gelu", "ce_partial", "ce_grad", "table", "swiglu", "rope", "bf16+="]
+            with open(args.gemm_table, "w") as fh:
+                fh.write(f"GEMM launches of {prof_steps} eager C2 steps by shape (CUDA events around each launch; peak {pk['tensor']:.0f} TFLOP/s)\n\n")
+                fh.write("| M | N | K | A | B | epilogue | split-K | launches | ms/step | TFLOP/s | frac | ms lost vs peak /step |\n|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+                for tag, (c, ms, f) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                    tf = f / (ms * 1e-3) / 1e12
+                    fh.write(f"| {tag[0]} | {tag[1]} | {tag[2]} | {'K' if tag[3] else 'MN'} | {'K' if tag[4] else 'MN'} | {EPI[tag[5]]} | {tag[6]} | {c // prof_steps} | "
+                             f"{ms / prof_steps:.3f} | {tf:.0f} | {tf / pk['tensor']:.2f} | {(ms - f / (pk['tensor'] * 1e12) * 1e3) / prof_steps:.3f} |\n")
         ach = flops / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
         out = {
             "metric": METRIC, "value": world * n_inter / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -262,6 +275,7 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--cpu-rows", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-table", default=None, help="write a per-shape table of the GEMM launches (markdown) to this path")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

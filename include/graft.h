@@ -136,8 +136,11 @@ typedef struct {
    * rows >= ceil(*m_count/128)*128 of C are not computed (left untouched); the K range is
    * cut to ceil(*k_count/128)*128.  Operand rows inside the rounded range must be finite. */
   const int32_t* m_count; const int32_t* k_count;
-  /* ROPE epilogue: tables [max_pos, 32] fp32; position = rope_pos[m] if given else m % rope_row_len */
+  /* ROPE epilogue: tables [max_pos, 32] fp32; position = rope_pos[m] if given else m % rope_row_len.
+   * rope_t_stride > 0: the tables are transposed, [32, rope_t_stride] (element (pos, pair) at pair*rope_t_stride + pos):
+   * the 32 rows a warp finishes together are consecutive positions, so every table read is one coalesced line. */
   const float* rope_cos; const float* rope_sin; const int32_t* rope_pos; int rope_cols; int rope_row_len;
+  int rope_t_stride;
 } graft_gemm_args;
 int64_t graft_gemm_scratch_bytes(const graft_gemm_args* g);
 int graft_gemm_bf16(const graft_gemm_args* g, void* scratch, int64_t scratch_bytes, graft_stream_t stream);

@@ -47,6 +47,7 @@ class GemmArgs(C.Structure):
         ("n_offset", i32), ("split_k", C.c_int),
         ("m_count", vp), ("k_count", vp),
         ("rope_cos", vp), ("rope_sin", vp), ("rope_pos", vp), ("rope_cols", C.c_int), ("rope_row_len", C.c_int),
+        ("rope_t_stride", C.c_int),
     ]
 
 
@@ -232,8 +233,9 @@ def gemm(A, B, Cout, M, N, K, *, a_kmajor=True, b_kmajor=True, lda=None, ldb=Non
         g.m_count = vp(m_count.data_ptr())
     if k_count is not None:
         g.k_count = vp(k_count.data_ptr())
-    if rope is not None:  # dict(cos=, sin=, cols=, row_len=, pos=None)
+    if rope is not None:  # dict(cos=, sin=, cols=, row_len=, pos=None, t_stride=0: tables transposed [32, t_stride])
         g.rope_cos, g.rope_sin = vp(rope["cos"].data_ptr()), vp(rope["sin"].data_ptr())
+        g.rope_t_stride = int(rope.get("t_stride", 0))
         g.rope_cols, g.rope_row_len = rope["cols"], rope.get("row_len", 0)
         if rope.get("pos") is not None:
             g.rope_pos = vp(rope["pos"].data_ptr())
@@ -246,7 +248,7 @@ def gemm(A, B, Cout, M, N, K, *, a_kmajor=True, b_kmajor=True, lda=None, ldb=Non
     _check(lib.graft_gemm_bf16(C.byref(g), ptr(ws), i64(ws.numel() if ws is not None else 0), stream()), "graft_gemm_bf16")
     if GEMM_EVENTS is not None:
         e1.record()
-        GEMM_EVENTS.append((e0, e1, 2.0 * M * N * K))
+        GEMM_EVENTS.append((e0, e1, 2.0 * M * N * K, (M, N, K, int(a_kmajor), int(b_kmajor), int(epilogue), int(split_k))))
 
 
 def ce_nblocks(N):

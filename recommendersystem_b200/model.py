@@ -163,6 +163,10 @@ class Transformer(nn.Module):
         ang = torch.outer(torch.arange(n, dtype=torch.float32), inv)
         self.register_buffer("freqs_cos", torch.cos(ang), persistent=False)
         self.register_buffer("freqs_sin", torch.sin(ang), persistent=False)
+        # the same tables transposed ([hd/2, n]) for the qkv GEMM's RoPE epilogue: a warp's 32 rows are consecutive
+        # positions, so it reads one 128-byte line per (pair, table) instead of 32 scattered 16-byte pieces
+        self.register_buffer("freqs_cos_t", torch.cos(ang).t().contiguous(), persistent=False)
+        self.register_buffer("freqs_sin_t", torch.sin(ang).t().contiguous(), persistent=False)
 
 
 # ------------------------------------------------------------------------------
@@ -309,7 +313,9 @@ class _ClozeStep(torch.autograd.Function):
             qkv = _bf16((T, QKV), dev)
             lora = None
             if not P.lora:
-                L.gemm(xn, qkv_w, qkv, T, QKV, dm, epilogue=L.EPI_ROPE, rope=dict(cos=cos, sin=sin, cols=(H + G) * 64, row_len=2 * S))
+                tr = model.transformers
+                L.gemm(xn, qkv_w, qkv, T, QKV, dm, epilogue=L.EPI_ROPE,
+                       rope=dict(cos=tr.freqs_cos_t, sin=tr.freqs_sin_t, t_stride=int(tr.freqs_cos_t.shape[1]), cols=(H + G) * 64, row_len=2 * S))
             else:
                 # LoRA on q and v (ref:263-271): q += 2 * B_q (A_q drop(x)), v likewise; rank padded 8 -> 64 with
                 # zeros so the two skinny GEMMs use the regular tiles; the factor 2 = alpha/r is folded into B

@@ -137,6 +137,14 @@ def test_gemm_fused_swiglu_and_rope_epilogues():
     L.gemm(X, Wq, ref, T, N, K); L.rope(ref, H + G, row_len, cos, sin, pos=pos)
     L.gemm(X, Wq, got, T, N, K, epilogue=L.EPI_ROPE, rope=dict(cos=cos, sin=sin, cols=(H + G) * 64, pos=pos))
     assert torch.equal(got, ref)
+    # transposed tables ([32, max_pos]: coalesced reads), both position modes: bit-identical
+    cos_t, sin_t = cos.t().contiguous(), sin.t().contiguous()
+    got.zero_()
+    L.gemm(X, Wq, got, T, N, K, epilogue=L.EPI_ROPE, rope=dict(cos=cos_t, sin=sin_t, t_stride=row_len, cols=(H + G) * 64, pos=pos))
+    assert torch.equal(got, ref)
+    L.gemm(X, Wq, ref, T, N, K); L.rope(ref, H + G, row_len, cos, sin)
+    L.gemm(X, Wq, got, T, N, K, epilogue=L.EPI_ROPE, rope=dict(cos=cos_t, sin=sin_t, t_stride=row_len, cols=(H + G) * 64, row_len=row_len))
+    assert torch.equal(got, ref)
 
 
 def test_gemm_lora_shapes_and_bf16_accum():

@@ -189,6 +189,9 @@ def main():
     cosb, sinb = torch.cos(ang).to(dev).contiguous(), torch.sin(ang).to(dev).contiguous()
     ms = timer(lambda: L.gemm(A, Wq, qkv_f, T, QKV, d, epilogue=L.EPI_ROPE, rope=dict(cos=cosb, sin=sinb, cols=(H + G) * 64, row_len=2 * S)))
     rec("gemm qkv proj + fused RoPE epilogue", ms, flops=2.0 * T * QKV * d, note=f"{T}x{QKV}x{d}")
+    cost, sint = cosb.t().contiguous(), sinb.t().contiguous()
+    ms = timer(lambda: L.gemm(A, Wq, qkv_f, T, QKV, d, epilogue=L.EPI_ROPE, rope=dict(cos=cost, sin=sint, t_stride=2 * S, cols=(H + G) * 64, row_len=2 * S)))
+    rec("gemm qkv proj + fused RoPE epilogue, transposed tables (step path)", ms, flops=2.0 * T * QKV * d, note=f"{T}x{QKV}x{d}")
     del A, Wg, gu_f, act_f, Wq, qkv_f
     gemm_case("gemm w2 (down)", T, d, I)
     gemm_case("gemm out proj", T, d, H * 64)
