@@ -740,11 +740,13 @@ class RecommenderModel(nn.Module):
         return torch.nn.functional.dropout(torch.ones(shape, dtype=torch.float32, device=dev), 0.1, True).reshape(-1)
 
     def _meta_bf16(self):
-        """bf16 copy of the frozen metadata table, rows padded to a 16-byte pitch for TMA."""
+        """bf16 copy of the frozen metadata table, rows zero-padded to a multiple of 64 columns: the row pitch is then a
+        multiple of 128 bytes, so every 128-byte row of a TMA box is one aligned line (a 16-byte-aligned pitch made each
+        box row straddle two lines: twice the requests for the 1.2 GB operand of the item-table GEMMs)."""
         w = self.item_embedding.metadata_embedding.embedding.weight
         key = (w.data_ptr(), w._version, str(w.device))
         if self._meta_cache is None or self._meta_cache[0] != key:
-            Mp = (w.shape[1] + 7) // 8 * 8
+            Mp = (w.shape[1] + 63) // 64 * 64
             buf = torch.empty((w.shape[0], Mp), dtype=torch.bfloat16, device=w.device)
             L.cast_pad_rows(w.detach(), buf)
             self._meta_cache = (key, buf, Mp)
