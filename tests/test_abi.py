@@ -90,3 +90,24 @@ def test_state_dict_surface(golden):
     assert {"watch_head." + k for k in golden["param"] if k.startswith("item_embedding.")} <= keys
     frozen = [n for n, p in model.named_parameters() if not p.requires_grad]
     assert frozen == ["item_embedding.metadata_embedding.embedding.weight"]
+
+
+def test_gemm_split_plan_host():
+    """The automatic split-K plan (host-side cost model, gemm_sm100.cu: pick_auto) for the backward's dW shapes at C2
+    on a 148-SM part, read back through graft_gemm_scratch_bytes (= splits * M * N * 4); no kernel is launched."""
+    lib = L.load()
+
+    def splits(M, N, K, epilogue=L.EPI_F32, split_k=-1):
+        g = L.GemmArgs()
+        g.M, g.N, g.K, g.epilogue, g.split_k = M, N, K, epilogue, split_k
+        need = lib.graft_gemm_scratch_bytes(ctypes.byref(g))
+        assert need % (M * N * 4) == 0
+        return need // (M * N * 4)
+
+    assert splits(768, 2112, 131072) == 8      # 54 tiles -> 432 work units = 2.9 rounds of 148 SMs (was 2 splits: 108 units)
+    assert splits(4224, 768, 131072) == 7      # 99 tiles -> 693 units = 4.7 rounds (was unsplit: 99 units)
+    assert splits(1536, 768, 131072) == 4      # 36 tiles -> 144 units
+    assert splits(768, 768, 131072) == 8       # 18 tiles -> 144 units
+    assert splits(768, 6148, 100001) == 0      # 128-wide tiles: 294 tiles = 2 full rounds, no split needed
+    assert splits(768, 2112, 131072, split_k=0) == 0 and splits(768, 2112, 131072, split_k=3) == 3
+    assert splits(768, 2112, 131072, epilogue=L.EPI_BF16) == 0   # only fp32 outputs are split
