@@ -1,24 +1,31 @@
 // Jagged softmax attention, GQA-pair kernels for sm_100a (head_dim 64).
 //
-// Two query heads that share one K/V head run in one CTA of 17 warps:
+// Two query heads that share one K/V head run in one CTA of 18 warps:
 //   warps 0-15 : softmax/elementwise.  warp w -> head (w>>3), column half ((w>>2)&1),
 //                TMEM lane quarter (w&3).  A thread owns one accumulator row (TMEM lane)
 //                and one half of the tile's columns, so a head's 128x128 (or 128x64) tile
 //                is spread over 8 warps and every scheduler has 4 warps to hide latency.
-//   warp 16    : issue warp, one thread: TMA loads + tcgen05.mma.
-// K/V tiles are loaded once for both heads; while one head's warps do exp2/pack the
-// tensor pipe runs the other head's MMAs; a head's next S tile is issued right behind
-// its PV, and the O update of tile j is deferred until after the row max of tile j+1
-// so nobody waits on a just-issued MMA.  mbarrier protocol per head h:
+//   warp 16    : MMA issue warp: warp-uniform control flow, all lanes poll the mbarriers, one
+//                elect.sync-chosen lane issues tcgen05.mma / tcgen05.commit.  It waits for data
+//                only (P / dS from the softmax warps, tiles from the load warp), never for an
+//                MMA to retire.
+//   warp 17    : TMA load warp (one elected thread): operand tiles run stages ahead; stages are
+//                handed back to it by tcgen05.commit on per-stage mbarriers.
+// K/V tiles are loaded once for both heads; while one head's warps do exp2/pack the tensor
+// pipe runs the other head's MMAs; a head's next score tile is issued right behind the
+// arrival of its P / dS, ahead of the accumulate MMAs.  The bf16 P / dS / Pt / dSt never
+// touch shared memory: tcgen05.st into TMEM columns 384..511, consumed as the MMA's A
+// operand.  mbarrier protocol per head h:
 //   bar_s[h]  : tcgen05.commit -> S_h (and dP_h) of the current tile is in TMEM
-//   bar_p[h]  : 256 arrivals   -> P_h/dS_h is in smem, S_h has been read
-//   bar_pv[h] : tcgen05.commit -> the MMAs that read P_h/dS_h retired
+//   bar_p[h]  : 8 arrivals (one per warp) -> P_h/dS_h is written, S_h has been read
+//   bar_pv / bar_dq / bar_acc[h] : tcgen05.commit -> the MMAs that read P_h/dS_h retired
 // Visibility handling (run ranges + ballot words) is the same as attn_sm100.cu.
+// How this structure was arrived at (timelines, UMMA rates): profiles/r01k_notes.md.
 #include "attn_common.cuh"
 
 namespace graft {
 
-constexpr int PAIR_THREADS = 576;  // 16 softmax warps, MMA issue warp (16), TMA load warp (17; backward kernels)
+constexpr int PAIR_THREADS = 576;  // 16 softmax warps, MMA issue warp (16), TMA load warp (17)
 // ATTN_TS: which kernels keep the bf16 probabilities / score gradients in tensor memory and feed them to
 // tcgen05.mma as the A operand (bit 0 forward P, bit 1 dQ kernel dS, bit 2 dK/dV kernel Pt and dSt) instead of
 // staging them in shared memory: no st.shared / async-proxy fence in the softmax warps, and the accumulate MMAs
@@ -486,7 +493,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
 
 // ================================================================ dQ ==========
 // CTA = (128-query tile, head pair); 64-key tiles; a thread owns a row and 32 of the 64 columns.
-// smem per head: Q 16K | dO 16K | dS 16K ; shared: K 2x8K | V 2x8K ; ids ; barriers
+// smem per head: Q 16K | dO 16K | dS 16K (only used when ATTN_TS bit 1 is off) ; shared: K 3x8K | V 3x8K ; ids ; barriers
 constexpr int DQ_KV_STAGES = 3;
 constexpr int DQP_SMEM = 2 * 49152 + 2 * DQ_KV_STAGES * 8192 + 2 * 2 * 64 * 4 + 2 * 2 * 2 * 4 + 256 + 1024;
 
