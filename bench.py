@@ -127,8 +127,7 @@ class ClockSampler:
 def gpu_bench(args):
     from recommendersystem_b200 import lib as L
     from recommendersystem_b200.model import RecommenderModel
-    from recommendersystem_b200.optim import FlatAdamW
-    from oracle.cloze_oracle import default_task_weights  # constants only (transformer.py:379-406)
+    from recommendersystem_b200.optim import FlatAdamW, make_task_weights
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -145,7 +144,7 @@ def gpu_bench(args):
     model.load_pretrained_embeddings(metadata=synthetic.make_metadata(cfg))
     model = model.to(dev)
     opt = FlatAdamW(model, lr=cfg["learning_rate"])
-    tw = default_task_weights()
+    tw = make_task_weights()
     S = cfg["max_sequence_length"]
     n_inter = rows * S
 

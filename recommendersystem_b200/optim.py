@@ -16,6 +16,25 @@ import torch.distributed as dist
 from . import lib as L
 
 
+# loss scales of the four tasks, order [0.watch, 0.rating, 1.watch, 1.rating] (transformer.py:381-390)
+TASK_LOSS_SCALE = (4.618602403897067, 1.1958987168236102, 2.5443243303769867, 1.0527565486045412)
+
+
+def make_task_weights(finetune_medium=None, finetune_metric=None):
+    """`make_task_weights` of the reference trainer (transformer.py:379-406): per-task weights of the step's loss sum,
+    order [0.watch, 0.rating, 1.watch, 1.rating].  Pre-train: anime 4x manga, watch 4x rating; finetune: one
+    (medium, metric) pair carries all the weight.  Each weight is normalised to sum 1, then divided by the task's scale."""
+    metrics = ("watch", "rating")
+    balance = []
+    for medium in (0, 1):
+        wm = (0.25, 1.0)[medium] if finetune_medium is None else float(medium == finetune_medium)
+        for metric in metrics:
+            wk = (1.0, 0.25)[metrics.index(metric)] if finetune_metric is None else float(metric == finetune_metric)
+            balance.append(wm * wk)
+    total = sum(balance)
+    return [(b / total) / s for b, s in zip(balance, TASK_LOSS_SCALE)]
+
+
 def wsd_lr_factor(step, warmup_steps, total_steps, decay_ratio=0.1, final_ratio=0.1):
     """Warm-up / stable / decay multiplier of the reference's pre-train schedule (transformer.py:310-328
     WSDScheduler, used as LambdaLR at :344-347: warm-up 2000 steps, last 10 % decays linearly to 0.1x).

@@ -115,3 +115,16 @@ def test_wsd_schedule_matches_reference_formula():
         ref = WSD(w, t, 0.1, 0.1)
         for s in list(range(0, min(t, 60))) + [t // 2, t - 3, t - 1, t, t + 5]:
             assert wsd_lr_factor(s, w, t) == ref(s), (w, t, s)
+
+
+def test_make_task_weights_matches_reference_formula():
+    """optim.make_task_weights (the product's mirror of transformer.py:379-406) == the oracle's restatement, for the
+    pre-train weights and every finetune (medium, metric) choice."""
+    from oracle.cloze_oracle import default_task_weights
+    from recommendersystem_b200.optim import make_task_weights
+    for fm in (None, 0, 1):
+        for fk in (None, "watch", "rating"):
+            a, b = make_task_weights(fm, fk), default_task_weights(fm, fk)
+            assert len(a) == 4 and all(abs(x - y) <= 1e-15 * max(1.0, abs(y)) for x, y in zip(a, b)), (fm, fk, a, b)
+    w = make_task_weights()
+    assert abs(sum(x * s for x, s in zip(w, (4.618602403897067, 1.1958987168236102, 2.5443243303769867, 1.0527565486045412))) - 1.0) < 1e-12
