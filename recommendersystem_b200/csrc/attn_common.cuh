@@ -18,6 +18,7 @@ struct AttnDev {
   __nv_bfloat16* dqkv; long long ld;         // bwd output (layout of qkv)
   int mode;                                  // 0 softmax, 1 point-wise SiLU (pair kernels only)
   const float* rope_cos; const float* rope_sin;  // bwd (optional): [max_pos, 32] tables; dq / dk are stored un-rotated
+  unsigned int* flags;                       // the library's status word (graft_status_flags)
 };
 
 // byte offset of (row, 16-byte chunk) inside a [rows x 128 B] SW128 K-major tile

@@ -26,10 +26,13 @@ class GraphedStep:
         self.graph = None
         self.losses = None
         self.launches = 0
+        # the graph bakes in the raw pointers of the workspaces its kernels borrowed (split-K partials, sort space,
+        # reduction partials): they live in a scope this object owns, so no later eager call can replace or free them
+        self.scratch = L.ScratchScope()
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
-        with torch.cuda.stream(side):  # warm-up on a side stream: allocator pools, lazy caches, function attributes
+        with self.scratch, torch.cuda.stream(side):  # warm-up on a side stream: allocator pools, lazy caches, function attributes
             for _ in range(warmup):
                 self._load(example_batch)
                 self._eager()
@@ -38,8 +41,9 @@ class GraphedStep:
         self._load(example_batch)
         g = torch.cuda.CUDAGraph()
         before = L.LAUNCHES
-        with torch.cuda.graph(g):
+        with self.scratch, torch.cuda.graph(g):
             self.losses = self._eager()
+        self.scratch.frozen = True
         self.launches = L.LAUNCHES - before
         self.graph = g
 

@@ -38,15 +38,52 @@ def init_weights(module, std=0.006):
         module.weight.data[-1].fill_(0)
 
 
+def _need_cuda(t, what):
+    if not t.is_cuda:
+        raise L.GraftError(f"{what} has no CPU path: move the module and its inputs to a CUDA device")
+
+
+_BATCH_INT = ("userid", "token_mask_ids", "gender", "source", "matchedid", "status", "rope_input_pos")
+
+
+def _normalise_batch(d, device=None):
+    """Element types the kernels hard-code (ids Int32, time Float64, the rest Float32; `.position` is
+    int64 in the finetune loader, transformer.py:182-183).  The reference module indexes with whatever integer dtype it is
+    given; here a mismatch would be reinterpreted bit-wise, so every entry is converted (a no-op when it already
+    matches) and the dict is updated IN PLACE, like the step's other edits of `d`."""
+    for k in list(d):
+        v = d[k]
+        if k == "time":
+            want = torch.float64
+        elif k in _BATCH_INT or k.endswith(".position"):
+            want = torch.int32
+        else:
+            want = torch.float32
+        if v.dtype != want or (device is not None and v.device != device):
+            d[k] = v.to(device=device if device is not None else v.device, dtype=want)
+    return d
+
+
 # ------------------------------------------------------------------------------
 # Parameter containers.  They carry the reference's module/parameter names so
-# that checkpoints interchange; none of them computes.
+# that checkpoints interchange (SURVEY.md 8b).  The training step never calls
+# their forward (it is one fused autograd node, _ClozeStep); the embedding
+# modules still answer a direct call the way the reference's do, through the
+# same libgraft kernels and without autograd (Finetune/register.py:29 exports
+# the item table with `model.item_embedding(torch.arange(...))`).
 # ------------------------------------------------------------------------------
 class MaskedEmbedding(nn.Module):
     def __init__(self, vocab_size, embed_dim):
         super().__init__()
         self.vocab_size = vocab_size + 1  # last row = the "-1" (masked) row, ref:15-24
         self.embedding = nn.Embedding(self.vocab_size, embed_dim)
+
+    @torch.no_grad()
+    def forward(self, x):
+        """ref:23-24: rows of the table, -1 -> the last row.  Inference-only (no autograd)."""
+        w = self.embedding.weight
+        _need_cuda(w, "MaskedEmbedding.forward")
+        return L.embedding_gather(w.detach(), x.to(w.device))
 
 
 class ActionEmbedding(nn.Module):
@@ -59,6 +96,39 @@ class ActionEmbedding(nn.Module):
         self.gender_embedding = MaskedEmbedding(vs["gender"], 4)
         self.source_embedding = MaskedEmbedding(vs["source"], 4)
         self.linear = nn.Linear(32, config["embed_dim"])  # ref:36-49: 1+2+2+4+4+1+1+16+1 features
+        self.config = config
+
+    def kernel_args(self, d, W, N):
+        """graft_action_args for batch `d` (element types checked: the kernels hard-code them)."""
+        cfg = self.config
+        a = L.ActionArgs()
+        a.time = L.tptr(d["time"], torch.float64, "time")
+        a.gender, a.source, a.status = (L.tptr(d[k], torch.int32, k) for k in ("gender", "source", "status"))
+        a.rating, a.progress = L.tptr(d["rating"], torch.float32, "rating"), L.tptr(d["progress"], torch.float32, "progress")
+        a.periodic_cos, a.periodic_sin = L.ptr(W["ae.cos"]), L.ptr(W["ae.sin"])
+        a.gender_table, a.source_table, a.status_table = L.ptr(W["ae.gender"]), L.ptr(W["ae.source"]), L.ptr(W["ae.status"])
+        a.gender_rows, a.source_rows, a.status_rows = W["ae.gender"].shape[0], W["ae.source"].shape[0], W["ae.status"].shape[0]
+        a.weight, a.bias = L.ptr(W["ae.w"]), L.ptr(W["ae.b"])
+        a.min_ts, a.max_ts = float(cfg["min_ts"]), float(cfg["max_ts"])
+        a.rating_mean, a.rating_std = float(cfg["rating_mean"]), float(cfg["rating_std"])
+        a.n, a.d, a.round_bf16 = N, cfg["embed_dim"], 1
+        return a
+
+    @torch.no_grad()
+    def forward(self, d):
+        """ref:51-94 called on its own: [*, d] bf16 (what the autocast reference returns).  Inference-only."""
+        w = self.linear.weight
+        _need_cuda(w, "ActionEmbedding.forward")
+        d = _normalise_batch({k: d[k] for k in ("time", "gender", "source", "status", "rating", "progress")}, w.device)
+        shape = d["time"].shape
+        N = d["time"].numel()
+        W = {"ae.cos": self.periodic_time_cos, "ae.sin": self.periodic_time_sin, "ae.w": w, "ae.b": self.linear.bias,
+             "ae.status": self.status_embedding.embedding.weight, "ae.gender": self.gender_embedding.embedding.weight,
+             "ae.source": self.source_embedding.embedding.weight}
+        W = {k: v.detach() for k, v in W.items()}
+        x = torch.empty((2 * N, w.shape[0]), dtype=torch.float32, device=w.device)
+        L.action_embed(self.kernel_args(d, W, N), x, torch.empty((N, 32), dtype=torch.float32, device=w.device))
+        return x[1::2].to(torch.bfloat16).view(*shape, w.shape[0])
 
 
 class ItemEmbedding(nn.Module):
@@ -100,14 +170,80 @@ class ItemEmbedding(nn.Module):
     def reject_fused_checkpoint(module, state_dict, prefix, *args):
         assert (prefix + "fused_embedding") not in state_dict
 
+    # ---- kernels' view of the tables --------------------------------------------------------
+    _weights_version = 0   # bumped by optim.FlatAdamW.step: its raw-pointer updates do not touch tensor._version
+    _meta_cache = None
+    _table_cache = None
+
+    def meta_bf16(self):
+        """bf16 copy of the frozen metadata table, rows zero-padded to a multiple of 64 columns: the row pitch is then a
+        multiple of 128 bytes, so every 128-byte row of a TMA box is one aligned line (a 16-byte-aligned pitch made each
+        box row straddle two lines: twice the requests for the 1.2 GB operand of the item-table GEMMs)."""
+        w = self.metadata_embedding.embedding.weight
+        key = (w.data_ptr(), w._version, str(w.device))
+        if self._meta_cache is None or self._meta_cache[0] != key:
+            Mp = (w.shape[1] + 63) // 64 * 64
+            buf = torch.empty((w.shape[0], Mp), dtype=torch.bfloat16, device=w.device)
+            L.cast_pad_rows(w.detach(), buf)
+            self._meta_cache = (key, buf, Mp)
+        return self._meta_cache[1], self._meta_cache[2]
+
+    @torch.no_grad()
+    def table(self):
+        """[V+1, d] fp32 = ItemEmbedding.fuse() (ref:120-133): id rows + bf16(metadata . Wp^T + bp); the buffer itself when
+        fused.  Cached until a weight changes (tensor versions + the optimiser's step counter)."""
+        if self.fused:
+            return self.fused_embedding
+        ew, pw, pb = self.matchedid_embedding.embedding.weight, self.projection_layer.weight, self.projection_layer.bias
+        _need_cuda(ew, "ItemEmbedding")
+        key = (ew.data_ptr(), ew._version, pw.data_ptr(), pw._version, pb._version, ItemEmbedding._weights_version, str(ew.device))
+        if self._table_cache is None or self._table_cache[0] != key:
+            meta16, Mp = self.meta_bf16()
+            dm = ew.shape[1]
+            pw16 = torch.empty((dm, Mp), dtype=torch.bfloat16, device=ew.device); L.cast_pad_rows(pw.detach(), pw16)
+            tab = torch.empty(ew.shape, dtype=torch.float32, device=ew.device)
+            L.gemm(meta16, pw16, tab, ew.shape[0], dm, Mp, epilogue=L.EPI_TABLE, resid=ew.detach(), bias=pb.detach())
+            self._table_cache = (key, tab)
+        return self._table_cache[1]
+
+    @torch.no_grad()
+    def forward(self, x):
+        """ref:139-145 called on its own (Finetune/register.py:29): rows of the fused table, [*x.shape, d] fp32.
+        Inference-only: the training step differentiates the table inside _ClozeStep."""
+        tab = self.table()
+        _need_cuda(tab, "ItemEmbedding.forward")
+        return L.embedding_gather(tab, x.to(tab.device))
+
 
 class DualItemEmbedding(nn.Module):
     """Weight-tied cloze head: registers the same ItemEmbedding again (ref:148-151,354),
     which is why state_dict carries watch_head.item_embedding.* aliases."""
 
-    def __init__(self, item_embedding):
+    def __init__(self, item_embedding, v0=None):
         super().__init__()
         self.item_embedding = item_embedding
+        self._v0 = v0  # catalog size of medium 0 (manga): the tied table holds medium 0 rows first (ref:155-161)
+
+    @torch.no_grad()
+    def forward(self, inputs):
+        """ref:153-170 called on its own: (x [rows, d], medium) -> logits [rows, K_medium] bf16 = x . items^T with the
+        catalog slice of the tied item table (no bias, no temperature).  Inference-only; the training step never
+        materialises this matrix (cross-entropy is fused into the logit GEMM's epilogue)."""
+        x, medium = inputs
+        ie = self.item_embedding
+        tab = ie.table()
+        _need_cuda(tab, "DualItemEmbedding.forward")
+        V0 = self._v0
+        assert medium in (0, 1)
+        lo, hi = (0, V0) if medium == 0 else (V0, ie.vocab_size)
+        x2 = x.reshape(-1, x.shape[-1]).to(tab.device)
+        rows, dm, K = x2.shape[0], x2.shape[1], hi - lo
+        x16 = x2.to(torch.bfloat16).contiguous()
+        items16 = torch.empty((K, dm), dtype=torch.bfloat16, device=tab.device); L.cast_bf16(tab[lo:hi], items16)
+        ldc = (K + 7) // 8 * 8
+        out = torch.empty((rows, ldc), dtype=torch.bfloat16, device=tab.device)
+        L.gemm(x16, items16, out, rows, K, dm, ldc=ldc)
+        return out[:, :K].view(*x.shape[:-1], K)
 
 
 class RMSNorm(nn.Module):
@@ -207,10 +343,15 @@ class _Params:
 
 def _attn_mode(cfg):
     """config["attention"]: "softmax" (the reference, default) or "silu" (HSTU-style point-wise attention,
-    BASELINE configs[2]; not in the reference - defined by oracle/cloze_oracle.py:silu_pointwise_attention)."""
+    BASELINE configs[2]; not in the reference - defined by oracle/cloze_oracle.py:silu_pointwise_attention).
+    config["attention_safe"] (softmax only): forward with the online-softmax kernel - exact for any score range; the
+    default fixed-reference kernel is exact while no score exceeds its row's first-tile maximum by > 69 nats and
+    raises lib.FLAG_ATTN_RANGE otherwise (lib.check_status())."""
     kind = cfg.get("attention", "softmax")
     assert kind in ("softmax", "silu"), kind
-    return L.ATTN_SILU if kind == "silu" else L.ATTN_SOFTMAX
+    if kind == "silu":
+        return L.ATTN_SILU
+    return L.ATTN_SOFTMAX | (L.ATTN_SAFE if cfg.get("attention_safe") else 0)
 
 
 def _bf16(shape, dev):
@@ -240,6 +381,12 @@ class _ClozeStep(torch.autograd.Function):
         nl = cfg["num_layers"]
         assert dm // H == 64, "libgraft attention is built for head_dim 64 (as the reference configs use)"
         assert I % 64 == 0, "intermediate_dim must be a multiple of 64 (fused gate/up tile layout)"
+        assert (2 * S) % 128 == 0, "rows must hold a multiple of 64 positions (128-token attention tiles)"
+        # the reference raises a broadcast error when a row is longer than the RoPE table (ref:182-190, 321-322)
+        assert 2 * S <= model.transformers.freqs_cos.shape[0], "row longer than the RoPE table (2 * max_sequence_length)"
+        # run-based visibility == the reference's userid equality only if no userid recurs inside a row:
+        # checked on the device, reported through the status word (lib.check_status) - no host sync in the step
+        L.check_rows(d["userid"], count=False)
         QKV = (H + 2 * G) * 64
         V0 = cfg["vocab_sizes"]["0_matchedid"]
         Vt = V0 + cfg["vocab_sizes"]["1_matchedid"]
@@ -275,7 +422,7 @@ class _ClozeStep(torch.autograd.Function):
             table, table16 = model._fused_tables()
             Mp = 0
         else:
-            meta16, Mp = model._meta_bf16()
+            meta16, Mp = model.item_embedding.meta_bf16()
             pw16 = _bf16((dm, Mp), dev); L.cast_pad_rows(W["ie.pw"], pw16)
             table = _f32((Vt + 1, dm), dev)
             L.gemm(meta16, pw16, table, Vt + 1, dm, Mp, epilogue=L.EPI_TABLE, resid=W["ie.id"], bias=W["ie.pb"])
@@ -287,7 +434,7 @@ class _ClozeStep(torch.autograd.Function):
         x = _f32((T, dm), dev)
         mid = d["matchedid"].reshape(-1)
         L.item_gather(table, mid, x)
-        aa = model._action_args(d, W, N)
+        aa = model.action_embedding.kernel_args(d, W, N)
         feats = _f32((N, 32), dev)
         L.action_embed(aa, x, feats)
         sv["feats"], sv["aa"], sv["mid"] = feats, aa, mid
@@ -598,7 +745,7 @@ class _ClozeStep(torch.autograd.Function):
         dpb = _f32((dm,), dev); L.colsum(dtable, dpb)
         G_["ie.pb"] = dpb
         dt16 = _bf16((Vt + 1, dm), dev); L.cast_bf16(dtable, dt16)
-        meta16, _ = model._meta_bf16()
+        meta16, _ = model.item_embedding.meta_bf16()
         Mraw = cfg["metadata_emb_size"]
         dpw = _f32((dm, Mraw), dev)
         L.gemm(dt16, meta16, dpw, dm, Mraw, Vt + 1, a_kmajor=False, lda=dm, b_kmajor=False, ldb=Mp, epilogue=L.EPI_F32, split_k=-1)
@@ -626,12 +773,12 @@ def _inference_hidden(model, d):
     dm, H, G, I = cfg["embed_dim"], cfg["num_heads"], cfg["num_kv_heads"], cfg["intermediate_dim"]
     assert dm // H == 64 and I % 64 == 0 and (2 * S) % 128 == 0, "head_dim 64, FFN % 64, row length % 64 positions"
     QKV = (H + 2 * G) * 64
-    d = {k: (v if v.is_contiguous() else v.contiguous()) for k, v in d.items()}
+    d = _normalise_batch({k: (v if v.is_contiguous() else v.contiguous()) for k, v in d.items()})
     wts = model._inference_weights()
     table = wts["table"]
     x = _f32((T, dm), dev)
     L.item_gather(table, d["matchedid"].reshape(-1), x)
-    L.action_embed(model._action_args(d, W, N), x, _f32((N, 32), dev))
+    L.action_embed(model.action_embedding.kernel_args(d, W, N), x, _f32((N, 32), dev))
     tm_tok = torch.empty(T, dtype=torch.int32, device=dev); L.interleave_i32(d["token_mask_ids"].reshape(-1), tm_tok)
     seg_s, seg_e = L.token_segments(d["userid"])
     cos, sin = model.transformers.freqs_cos, model.transformers.freqs_sin
@@ -675,7 +822,7 @@ class RecommenderModel(nn.Module):
         self.action_embedding = ActionEmbedding(config)
         self.item_embedding = ItemEmbedding(config)
         self.transformers = Transformer(config)
-        self.watch_head = DualItemEmbedding(self.item_embedding)
+        self.watch_head = DualItemEmbedding(self.item_embedding, config["vocab_sizes"]["0_matchedid"])
         self.rating_head = nn.Sequential(
             nn.Linear(config["embed_dim"], config["embed_dim"]), nn.GELU(), nn.Linear(config["embed_dim"], 1))
         self.apply(init_weights)
@@ -688,7 +835,6 @@ class RecommenderModel(nn.Module):
         self._params_cache = None
         self._fused_cache = None
         self.lora_mask = None  # tests may inject f(layer, which, shape, device) -> dropout mask (0 or 1/0.9)
-        self._meta_cache = None
         self._taps = None
         self.mask_rand = None  # tests may inject f(shape, device) -> randval
         self._infer_cache = None
@@ -719,7 +865,8 @@ class RecommenderModel(nn.Module):
         with torch.no_grad():
             w.zero_()
             w[: mt.shape[0]].copy_(mt)
-        self._meta_cache = None
+        self.item_embedding._meta_cache = None
+        self.item_embedding._table_cache = None
 
     def _fused_tables(self):
         """finetune: the fused item table (fp32 buffer, ref:120-133) and its bf16 copy for the tied head."""
@@ -739,24 +886,11 @@ class RecommenderModel(nn.Module):
             return self.lora_mask(layer, which, shape, dev).reshape(-1).contiguous()
         return torch.nn.functional.dropout(torch.ones(shape, dtype=torch.float32, device=dev), 0.1, True).reshape(-1)
 
-    def _meta_bf16(self):
-        """bf16 copy of the frozen metadata table, rows zero-padded to a multiple of 64 columns: the row pitch is then a
-        multiple of 128 bytes, so every 128-byte row of a TMA box is one aligned line (a 16-byte-aligned pitch made each
-        box row straddle two lines: twice the requests for the 1.2 GB operand of the item-table GEMMs)."""
-        w = self.item_embedding.metadata_embedding.embedding.weight
-        key = (w.data_ptr(), w._version, str(w.device))
-        if self._meta_cache is None or self._meta_cache[0] != key:
-            Mp = (w.shape[1] + 63) // 64 * 64
-            buf = torch.empty((w.shape[0], Mp), dtype=torch.bfloat16, device=w.device)
-            L.cast_pad_rows(w.detach(), buf)
-            self._meta_cache = (key, buf, Mp)
-        return self._meta_cache[1], self._meta_cache[2]
-
     def _inference_weights(self):
         """bf16 operand copies of the block weights and the fused item table (= ItemEmbedding.fuse(),
         ref:120-133), rebuilt only when a parameter changed (inference weights are static)."""
         P = self._params
-        key = tuple((t.data_ptr(), t._version) for t in P.tensors) + (str(P.tensors[0].device),)
+        key = tuple((t.data_ptr(), t._version) for t in P.tensors) + (str(P.tensors[0].device), ItemEmbedding._weights_version)
         if self._infer_cache is not None and self._infer_cache[0] == key:
             return self._infer_cache[1]
         cfg = self.config
@@ -782,14 +916,7 @@ class RecommenderModel(nn.Module):
             w13v[:, 0].copy_(W[f"l{i}.w1"].detach().view(I // 64, 64, dm)); w13v[:, 1].copy_(W[f"l{i}.w3"].detach().view(I // 64, 64, dm))
             w2 = _bf16((dm, I), dev); L.cast_bf16(W[f"l{i}.w2"], w2)
             layers.append((qkv_w, o_w, w13, w2))
-        if P.fused:
-            table = self.item_embedding.fused_embedding
-        else:
-            meta16, Mp = self._meta_bf16()
-            pw16 = _bf16((dm, Mp), dev); L.cast_pad_rows(W["ie.pw"].detach(), pw16)
-            Vt1 = W["ie.id"].shape[0]
-            table = _f32((Vt1, dm), dev)
-            L.gemm(meta16, pw16, table, Vt1, dm, Mp, epilogue=L.EPI_TABLE, resid=W["ie.id"].detach(), bias=W["ie.pb"].detach())
+        table = self.item_embedding.table()
         w0_16 = _bf16((dm, dm), dev); L.cast_bf16(W["rh.w0"], w0_16)
         out = dict(layers=layers, table=table, w0_16=w0_16)
         self._infer_cache = (key, out)
@@ -819,20 +946,6 @@ class RecommenderModel(nn.Module):
         pred = _f32((rows,), dev)
         L.rating_pred(h1, W["rh.w2"], W["rh.b2"], pred)
         return pred.view(U, T2, 1).to(torch.bfloat16)
-
-    def _action_args(self, d, W, N):
-        cfg = self.config
-        a = L.ActionArgs()
-        a.time, a.gender, a.source, a.status = L.ptr(d["time"]), L.ptr(d["gender"]), L.ptr(d["source"]), L.ptr(d["status"])
-        a.rating, a.progress = L.ptr(d["rating"]), L.ptr(d["progress"])
-        a.periodic_cos, a.periodic_sin = L.ptr(W["ae.cos"]), L.ptr(W["ae.sin"])
-        a.gender_table, a.source_table, a.status_table = L.ptr(W["ae.gender"]), L.ptr(W["ae.source"]), L.ptr(W["ae.status"])
-        a.gender_rows, a.source_rows, a.status_rows = W["ae.gender"].shape[0], W["ae.source"].shape[0], W["ae.status"].shape[0]
-        a.weight, a.bias = L.ptr(W["ae.w"]), L.ptr(W["ae.b"])
-        a.min_ts, a.max_ts = float(cfg["min_ts"]), float(cfg["max_ts"])
-        a.rating_mean, a.rating_std = float(cfg["rating_mean"]), float(cfg["rating_std"])
-        a.n, a.d, a.round_bf16 = N, cfg["embed_dim"], 1
-        return a
 
     def mask_tokens(self, d):
         """ref:417-462 (pre-train branch): same draws, same in-place edits of `d`."""
@@ -878,6 +991,7 @@ class RecommenderModel(nn.Module):
         if not self.config["finetune"]:
             for k in d:
                 d[k] = d[k].reshape(-1, S)  # ref:495-496 (mutates the caller's dict, as the trainer expects)
+        _normalise_batch(d)
         d = self.mask_tokens(d)
         for k in d:
             if not d[k].is_contiguous():

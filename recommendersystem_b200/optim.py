@@ -96,6 +96,10 @@ class FlatAdamW:
 
     def step(self, lr=None):
         self.steps += 1
+        # graft_adamw updates the parameters through raw pointers, which does not bump tensor._version: tell the
+        # model-side caches (fused item table, bf16 inference weights) that every weight changed
+        from .model import ItemEmbedding
+        ItemEmbedding._weights_version += 1
         lr = self.lr if lr is None else lr
         self.all_reduce_grads()
         # clip_grad_norm_(params, max_norm): scale = min(1, max_norm / (norm + 1e-6)), on device

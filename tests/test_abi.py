@@ -111,3 +111,23 @@ def test_gemm_split_plan_host():
     assert splits(768, 6148, 100001) == 0      # 128-wide tiles: 294 tiles = 2 full rounds, no split needed
     assert splits(768, 2112, 131072, split_k=0) == 0 and splits(768, 2112, 131072, split_k=3) == 3
     assert splits(768, 2112, 131072, epilogue=L.EPI_BF16) == 0   # only fp32 outputs are split
+
+
+def test_exec_model_file_defines_reference_names_and_refuses_cpu():
+    """The model file is consumed by exec() (transformer.py:33-34, register.py:11-12, embed.py:164-165): the names it
+    must define, and a direct module call on CPU tensors fails loudly (no CPU fallback) instead of NotImplementedError."""
+    import numpy as np
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from recommendersystem_b200 import lib as L, synthetic
+    ns = {"torch": torch, "nn": nn, "F": F, "np": np}
+    with open(os.path.join(ROOT, "integration", "transformer.model.py")) as f:
+        exec(f.read(), ns)
+    assert ns["ALL_MEDIUMS"] == [0, 1] and ns["ALL_METRICS"] == ["watch", "rating"]
+    cfg, _ = synthetic.make_config("tiny")
+    model = ns["RecommenderModel"](dict(cfg, forward="inference"))
+    with pytest.raises(L.GraftError):
+        model.item_embedding(torch.arange(0, 4))
+    with pytest.raises(L.GraftError):
+        model.watch_head((torch.zeros(2, cfg["embed_dim"]), 0))
