@@ -229,7 +229,11 @@ typedef struct {
    * gradient of the un-rotated projections (the transpose rotation of transformer.model.py:182-190 at the
    * token's row position is applied before the store), so no separate inverse-RoPE pass is needed. */
   const float* rope_cos; const float* rope_sin;
+  /* [T/32] bitmaps of tm_tok == 0 and tm_tok == 1 (graft_token_mask_words): the GQA-pair forward kernel reads a key
+   * tile's mask ids as four words from these instead of staging 128 ids through shared memory per tile */
+  const uint32_t* tm_zero_words; const uint32_t* tm_one_words;
 } graft_attn_args;
+int graft_token_mask_words(const int32_t* tm_tok, int64_t T, uint32_t* zero_words, uint32_t* one_words, graft_stream_t stream);
 int graft_attn_fwd(const graft_attn_args* a, void* out_bf16, float* lse, graft_stream_t stream);
 /* dqkv has the layout of qkv; dout [T,H*64] bf16.  delta scratch [H,T] fp32 */
 int graft_attn_bwd(const graft_attn_args* a, const void* out_bf16, const void* dout_bf16, const float* lse,
@@ -260,6 +264,11 @@ int graft_ce_finish(const float* pmax, const float* psum, int n_blocks, const fl
  * graft_ce_finish runs with n_blocks = number of shards */
 int graft_ce_merge_partials(const float* pmax, const float* psum, int n_blocks, int rows, float* max_out, float* sum_out,
                             graft_stream_t stream);
+/* retrieval scoring of the embedding server, Finetune/embed.jl:86-90 compute_retrieval: softmax(W u)[idxs].  logits
+ * [rows, ld] bf16 = user rows x catalog slice (graft_gemm_bf16), row_max / row_sum from the CE_PARTIAL epilogue merged
+ * by graft_ce_merge_partials; out [rows, n_out] fp32 = probabilities of columns idx[0..n_out) (idx NULL: all columns) */
+int graft_softmax_gather(const void* logits_bf16, int64_t ld, int rows, const float* row_max, const float* row_sum,
+                         const int32_t* idx, int64_t n_out, float* out, graft_stream_t stream);
 /* rating head tail, transformer.model.py:355-359,391-401,521-526:
  * pred = bf16(h1 . w2 + b2); loss4 = moments for scale 1,0,-1 (loss4[0] is the
  * train MSE) and loss4[3] = max(sum w, 1e-8) */

@@ -19,6 +19,7 @@ struct AttnDev {
   int mode;                                  // 0 softmax, 1 point-wise SiLU (pair kernels only)
   const float* rope_cos; const float* rope_sin;  // bwd (optional): [max_pos, 32] tables; dq / dk are stored un-rotated
   unsigned int* flags;                       // the library's status word (graft_status_flags)
+  const uint32_t* zero_words; const uint32_t* one_words;  // [T/32] bitmaps of tm == 0 / tm == 1 (graft_token_mask_words)
 };
 
 // byte offset of (row, 16-byte chunk) inside a [rows x 128 B] SW128 K-major tile

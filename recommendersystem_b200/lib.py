@@ -57,6 +57,7 @@ class AttnArgs(C.Structure):
         ("H", C.c_int), ("G", C.c_int), ("rows", C.c_int), ("row_len", C.c_int),
         ("tm_tok", vp), ("seg_start", vp), ("seg_end", vp), ("mode", C.c_int),
         ("rope_cos", vp), ("rope_sin", vp),
+        ("tm_zero_words", vp), ("tm_one_words", vp),
     ]
 
 
@@ -69,7 +70,8 @@ _lib = None
 # made so far; GEMM_EVENTS (a list, when profiling) collects (start, end, flops) CUDA
 # events around every GEMM launch on the current stream.
 LAUNCHES = 0
-GEMM_EVENTS = None
+GEMM_EVENTS = None   # [(start, end, capacity flops, tag, m_count tensor | None, k_count tensor | None)]
+ATTN_EVENTS = None   # [(start, end, "fwd" | "bwd", H, seg_start, seg_end)]
 _LAUNCHES_PER_CALL = {
     "graft_jagged_offsets": 2, "graft_action_embed": 2, "graft_action_embed_bwd": 5, "graft_scatter_add_sorted": 6,
     "graft_rmsnorm_bwd": 2, "graft_colsum": 2, "graft_attn_bwd": 3, "graft_ce_finish": 2, "graft_rating_tail": 2,
@@ -321,7 +323,9 @@ def gemm(A, B, Cout, M, N, K, *, a_kmajor=True, b_kmajor=True, lda=None, ldb=Non
     _check(lib.graft_gemm_bf16(C.byref(g), ptr(ws), i64(ws.numel() if ws is not None else 0), stream()), "graft_gemm_bf16")
     if GEMM_EVENTS is not None:
         e1.record()
-        GEMM_EVENTS.append((e0, e1, 2.0 * M * N * K, (M, N, K, int(a_kmajor), int(b_kmajor), int(epilogue), int(split_k))))
+        # device-side limits (the heads' masked-row counts) are kept so that the FLOPs can be booked from the rows that
+        # were actually computed, not from the launch's capacity
+        GEMM_EVENTS.append((e0, e1, 2.0 * M * N * K, (M, N, K, int(a_kmajor), int(b_kmajor), int(epilogue), int(split_k)), m_count, k_count))
 
 
 def ce_nblocks(N):
@@ -407,18 +411,38 @@ def attn_args(qkv, H, G, rows, row_len, tm_tok, seg_s, seg_e, mode=ATTN_SOFTMAX,
     a.qkv, a.ld, a.k_col, a.v_col = vp(qkv.data_ptr()), qkv.shape[1], H * 64, (H + G) * 64
     a.H, a.G, a.rows, a.row_len = H, G, rows, row_len
     a.tm_tok, a.seg_start, a.seg_end = ptr(tm_tok), ptr(seg_s), ptr(seg_e)
+    a._seg = (seg_s, seg_e)   # python-side only (bench instrumentation: sum of squared run lengths)
+    words = getattr(tm_tok, "_graft_mask_words", None)  # bitmaps of the mask ids: built once per tm_tok tensor (= per step)
+    if words is None:
+        T = tm_tok.numel()
+        words = torch.empty((2, T // 32), dtype=torch.int32, device=tm_tok.device)
+        _check(load().graft_token_mask_words(ptr(tm_tok), i64(T), ptr(words[0]), ptr(words[1]), stream()), "graft_token_mask_words")
+        tm_tok._graft_mask_words = words
+    a.tm_zero_words, a.tm_one_words = ptr(words[0]), ptr(words[1])
+    a._words = words
     a.mode = mode
     if rope is not None:  # (cos, sin) tables: the backward stores dq / dk already un-rotated
         a.rope_cos, a.rope_sin = ptr(rope[0]), ptr(rope[1])
     return a
 
 
+def _attn_timed(kind, a, call):
+    if ATTN_EVENTS is None:
+        return call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call()
+    e1.record()
+    ATTN_EVENTS.append((e0, e1, kind, int(a.H), a._seg[0], a._seg[1]))
+
+
 def attn_fwd(a: AttnArgs, out, lse2):
-    _check(load().graft_attn_fwd(C.byref(a), ptr(out), ptr(lse2), stream()), "graft_attn_fwd")
+    _attn_timed("fwd", a, lambda: _check(load().graft_attn_fwd(C.byref(a), ptr(out), ptr(lse2), stream()), "graft_attn_fwd"))
 
 
 def attn_bwd(a: AttnArgs, out, dout, lse2, dqkv, delta):
-    _check(load().graft_attn_bwd(C.byref(a), ptr(out), ptr(dout), ptr(lse2), ptr(dqkv), ptr(delta), stream()), "graft_attn_bwd")
+    _attn_timed("bwd", a, lambda: _check(load().graft_attn_bwd(C.byref(a), ptr(out), ptr(dout), ptr(lse2), ptr(dqkv), ptr(delta),
+                                                               stream()), "graft_attn_bwd"))
 
 
 # -------------------------------------------------------------------- heads --
@@ -453,6 +477,13 @@ def ce_finish(pmax, psum, n_blocks, tgt, lab, w, lse, coef, term, loss):
 def ce_merge_partials(pmax, psum, n_blocks, m_out, s_out):
     _check(load().graft_ce_merge_partials(ptr(pmax), ptr(psum), n_blocks, m_out.numel(), ptr(m_out), ptr(s_out), stream()),
            "graft_ce_merge_partials")
+
+
+def softmax_gather(logits, row_max, row_sum, idx, out):
+    rows, n_out = out.shape
+    _check(load().graft_softmax_gather(ptr(logits), i64(logits.stride(0)), rows, ptr(row_max), ptr(row_sum),
+                                       tptr(idx, torch.int32, "idx") if idx is not None else None, i64(n_out), ptr(out), stream()),
+           "graft_softmax_gather")
 
 
 def rating_tail(h1, w2, b2, lab, w, mean, pred, loss4):

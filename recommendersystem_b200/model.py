@@ -927,6 +927,36 @@ class RecommenderModel(nn.Module):
         What register.py:14-38 exports and what the tied head scores against."""
         return self._inference_weights()["table"]
 
+    @torch.no_grad()
+    def retrieval_scores(self, user_embedding, medium, idxs=None):
+        """Finetune/embed.jl:86-90 compute_retrieval: p = softmax(W_medium . u)[idxs] for a batch of user embeddings
+        ([U, d]: the final-norm state inference_forward(d, "retrieval") returns at the user's masked query token).  W is
+        the medium's slice of the fused item table (what register.py exports as "<medium>.watch.weight").  The softmax
+        statistics come from the logit GEMM's epilogue; returns [U, len(idxs) or K_medium] fp32."""
+        tab = self.item_embedding.table()
+        _need_cuda(tab, "retrieval_scores")
+        V0 = self.config["vocab_sizes"]["0_matchedid"]
+        lo, hi = (0, V0) if medium == 0 else (V0, self.item_embedding.vocab_size)
+        K, dm = hi - lo, tab.shape[1]
+        u = user_embedding.reshape(-1, dm).to(tab.device)
+        U = u.shape[0]
+        u16 = u.to(torch.bfloat16).contiguous()
+        items16 = _bf16((K, dm), tab.device); L.cast_bf16(tab[lo:hi], items16)
+        ldc = (K + 7) // 8 * 8
+        logits = _bf16((U, ldc), tab.device)
+        L.gemm(u16, items16, logits, U, K, dm, ldc=ldc)
+        nb = L.ce_nblocks(K)
+        pmax = _f32((nb, U), tab.device); psum = _f32((nb, U), tab.device)
+        tgt = _f32((U,), tab.device); pos = torch.zeros(U, dtype=torch.int32, device=tab.device)
+        L.gemm(u16, items16, None, U, K, dm, epilogue=L.EPI_CE_PARTIAL, ce=dict(pmax=pmax, psum=psum, tgt=tgt, target=pos))
+        rmax = _f32((U,), tab.device); rsum = _f32((U,), tab.device)
+        L.ce_merge_partials(pmax, psum, nb, rmax, rsum)
+        if idxs is not None:
+            idxs = torch.as_tensor(idxs, device=tab.device).to(torch.int32).contiguous()
+        out = _f32((U, K if idxs is None else idxs.numel()), tab.device)
+        L.softmax_gather(logits, rmax, rsum, idxs, out)
+        return out
+
     @torch.compiler.disable
     def inference_forward(self, d, task):
         """ref:531-538: retrieval -> final-norm token states [U, 2S, d]; ranking -> rating head

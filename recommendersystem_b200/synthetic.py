@@ -79,6 +79,21 @@ def make_config(name="C1", **over):
         )
         base["vocab_sizes"] = {"0_matchedid": 60000, "1_matchedid": 40000, "status": 9, "gender": 4, "source": 4}
         rows = 64
+    elif name in ("C3", "C4", "C4L", "C5"):
+        # BASELINE configs[2..4] = the C2 model under another objective / sharding / input distribution:
+        #   C3  HSTU-style rating model: point-wise SiLU attention, rating-only task weights (bench / tests pick the weights)
+        #   C4  vocab-parallel catalog logits + cross-entropy (needs world > 1 to differ from C2)
+        #   C4L the same with the 1,000,000-item catalog stress of SURVEY 8d (metadata width cut to 512 so that the frozen
+        #       metadata table, which is not what this config stresses, stays at 2 GB)
+        #   C5  daily-finetune-like input: short recent histories, Zipf 1.2 items (sampler_kwargs) - scatter-add stress
+        base, rows = make_config("C2")
+        if name == "C3":
+            base["attention"] = "silu"
+        if name in ("C4", "C4L"):
+            base["vocab_parallel"] = True
+        if name == "C4L":
+            base["vocab_sizes"] = {"0_matchedid": 600000, "1_matchedid": 400000, "status": 9, "gender": 4, "source": 4}
+            base["metadata_emb_size"] = 512
     elif name == "P":  # reference production shape, transformer.py:535-560
         base.update(
             max_sequence_length=1024, num_layers=8, num_heads=32, num_kv_heads=16, embed_dim=2048,
@@ -97,6 +112,13 @@ def make_config(name="C1", **over):
         raise KeyError(name)
     base.update(over)
     return base, rows
+
+
+def sampler_kwargs(name):
+    """HistorySampler settings that belong to a named workload."""
+    if name == "C5":  # histories of 5..64 positions packed back to back (~1900 users per 65,536-position batch), heavy duplicates
+        return dict(len_median=30.0, len_sigma=1.0, len_clip=(5, 64), zipf_s=1.2)
+    return {}
 
 
 # --------------------------------------------------------------------------- #

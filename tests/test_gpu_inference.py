@@ -65,3 +65,23 @@ def test_fused_item_table_is_fuse():
         torch.as_tensor(params["item_embedding.projection_layer.weight"]), torch.as_tensor(params["item_embedding.projection_layer.bias"]))
     assert float((t - ref).norm() / ref.norm()) < 3e-3
     assert torch.equal(t[-1], ref[-1].float()) or float((t[-1] - ref[-1]).abs().max()) < 1e-3  # mask row: id row + bias
+
+
+def test_retrieval_scores_match_softmax_of_catalog_logits():
+    """Finetune/embed.jl:86-90 compute_retrieval: softmax(W u)[idxs] with W = the exported item table slice."""
+    from recommendersystem_b200.testing import model_from_params
+    z, cfg, params = _load()
+    model = model_from_params(cfg, params, DEV).eval()
+    g = torch.Generator().manual_seed(4)
+    u = (torch.randn(5, cfg["embed_dim"], generator=g) * 2.0).to(DEV)
+    table = model.fused_item_table()
+    V0 = cfg["vocab_sizes"]["0_matchedid"]
+    for medium, (lo, hi) in enumerate(((0, V0), (V0, table.shape[0] - 1))):
+        want = torch.softmax(u @ table[lo:hi].t(), dim=-1)
+        got = model.retrieval_scores(u, medium)
+        assert got.shape == want.shape
+        assert float((got - want).norm() / want.norm()) < 1e-2
+        assert float((got.sum(-1) - 1).abs().max()) < 1e-2
+        idxs = torch.tensor([3, 0, hi - lo - 1, 7])
+        sel = model.retrieval_scores(u, medium, idxs)
+        assert float((sel - want[:, idxs.to(DEV)]).norm() / want[:, idxs.to(DEV)].norm()) < 1e-2

@@ -395,29 +395,34 @@ def _attn_run(qkv, uid, tm, rows, row_len, H, G, mode=L.ATTN_SOFTMAX):
     return a, out, lse2
 
 
-def test_attention_large_scores():
-    """Scores 30x larger than the N(0, .8) cases (no QK norm in the model: trained q.k can be large): softmax is nearly
-    one-hot, the fixed-reference forward and both backward kernels still match fp32 SDPA, no range flag."""
+@pytest.mark.parametrize("qk_scale,check_bwd", [(5.5, False), (3.0, True)])
+def test_attention_large_scores(qk_scale, check_bwd):
+    """Scores 30x (q, k x 5.5: std ~ 18 nats, range +-70) and 9x (x 3: peaked but not one-hot) larger than the N(0, .8)
+    cases - the model has no QK norm, trained q.k can be large.  The fixed-reference forward still matches fp32 SDPA
+    and raises no range flag; at 9x the backward kernels are checked too (at 30x the softmax is one-hot to fp32
+    precision and the true gradients vanish, so a relative comparison of dq / dk is meaningless there)."""
     rows, row_len, H, G = 2, 1024, 4, 2
     uid, tm, qkv = make_attn_case(rows, row_len, H, G, seed=21, long_runs=True)
     qkv = qkv.float()
-    qkv[:, :(H + G) * 64] *= 5.5  # q and k: scores x 30 (std ~ 18 nats, range +-70)
+    qkv[:, :(H + G) * 64] *= qk_scale
     qkv = qkv.bfloat16()
     L.status_flags(clear=True)
     a, out, lse2 = _attn_run(qkv, uid, tm, rows, row_len, H, G)
     q = qkv.clone().float().requires_grad_(True)
     ref_o, ref_lse = attn_reference(q, uid, tm, rows, row_len, H, G)
-    report("attn out x30", out, ref_o, 1e-2)
+    report("attn out large", out, ref_o, 1e-2)
     lse_nat = (lse2 * 0.6931471805599453).view(H, rows, row_len).permute(1, 0, 2)
-    report("attn lse x30", lse_nat, ref_lse, 1e-4)
+    report("attn lse large", lse_nat, ref_lse, 1e-4)
+    assert L.status_flags() & L.FLAG_ATTN_RANGE == 0
+    if not check_bwd:
+        return
     do = g_randn(rows * row_len, H * 64, seed=11).bfloat16()
     ref_o.backward(do.float())
     dqkv = torch.empty_like(qkv); delta = torch.empty(H, rows * row_len, device=DEV)
     L.attn_bwd(a, out, do, lse2, dqkv, delta)
-    report("attn dq x30", dqkv[:, :H * 64], q.grad[:, :H * 64], 3e-2)
-    report("attn dk x30", dqkv[:, H * 64:(H + G) * 64], q.grad[:, H * 64:(H + G) * 64], 3e-2)
-    report("attn dv x30", dqkv[:, (H + G) * 64:], q.grad[:, (H + G) * 64:], 3e-2)
-    assert L.status_flags() & L.FLAG_ATTN_RANGE == 0
+    report("attn dq large", dqkv[:, :H * 64], q.grad[:, :H * 64], 3e-2)
+    report("attn dk large", dqkv[:, H * 64:(H + G) * 64], q.grad[:, H * 64:(H + G) * 64], 3e-2)
+    report("attn dv large", dqkv[:, (H + G) * 64:], q.grad[:, (H + G) * 64:], 3e-2)
 
 
 @pytest.mark.parametrize("gap_nats,expect_flag", [(55.0, False), (250.0, True)])

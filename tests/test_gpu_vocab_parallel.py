@@ -98,6 +98,28 @@ def test_vocab_parallel_matches_replicated_world2():
     assert list(out) == [1] * world
 
 
+def _nccl_worker(rank, world, port, out):
+    os.environ["LOCAL_RANK"] = str(rank)
+    _worker(rank, world, port, out, backend="nccl", dev=f"cuda:{rank}")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (one rank per GPU over NCCL / NVLink)")
+def test_vocab_parallel_matches_replicated_world2_nccl():
+    """The same parity with one rank per GPU and the NCCL backend (ncclAllGather / AllToAll / ReduceScatter through
+    comm.py): runs wherever the box has two GPUs, e.g. `gpurun --gpus 2 -- python -m pytest tests -m gpu`."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Array("i", [0] * world)
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert list(out) == [1] * world
+
+
 if __name__ == "__main__":  # torchrun --nproc-per-node N tests/test_gpu_vocab_parallel.py : one rank per GPU over NCCL
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
