@@ -397,10 +397,10 @@ def _attn_run(qkv, uid, tm, rows, row_len, H, G, mode=L.ATTN_SOFTMAX):
 
 @pytest.mark.parametrize("qk_scale,check_bwd", [(5.5, False), (3.0, True)])
 def test_attention_large_scores(qk_scale, check_bwd):
-    """Scores 30x (q, k x 5.5: std ~ 18 nats, range +-70) and 9x (x 3: peaked but not one-hot) larger than the N(0, .8)
-    cases - the model has no QK norm, trained q.k can be large.  The fixed-reference forward still matches fp32 SDPA
-    and raises no range flag; at 9x the backward kernels are checked too (at 30x the softmax is one-hot to fp32
-    precision and the true gradients vanish, so a relative comparison of dq / dk is meaningless there)."""
+    """Scores 30x (q, k x 5.5: std ~ 18 nats, range +-70) and 9x (x 3) larger than the N(0, .8) cases - the model has no
+    QK norm, trained q.k can be large.  The fixed-reference forward still matches fp32 SDPA and raises no range flag; at
+    9x the backward kernels are checked too (at 30x the softmax is one-hot to fp32 precision and the true gradients
+    vanish: a relative comparison of dq / dk means nothing there)."""
     rows, row_len, H, G = 2, 1024, 4, 2
     uid, tm, qkv = make_attn_case(rows, row_len, H, G, seed=21, long_runs=True)
     qkv = qkv.float()
