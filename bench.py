@@ -286,7 +286,7 @@ def gpu_bench(args):
             for e0, e1, f, tag in gemm_ev:
                 a = agg.setdefault(tag, [0, 0.0, 0.0])
                 a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += f
-            EPI = ["bf16", "f32", "f32+=", "resid", "bias", "bias_gelu", "ce_partial", "ce_grad", "table", "swiglu", "rope", "bf16+="]
+            EPI = ["bf16", "f32", "f32+=", "resid", "bias", "bias_gelu", "ce_partial", "ce_grad", "table", "swiglu", "rope", "bf16+=", "swiglu_bwd"]
             with open(args.gemm_table, "w") as fh:
                 fh.write(f"GEMM launches of {prof_steps} eager C2 steps by shape (CUDA events around each launch; peak {pk['tensor']:.0f} TFLOP/s)\n\n")
                 fh.write("| M | N | K | A | B | epilogue | split-K | launches | ms/step | TFLOP/s | frac | ms lost vs peak /step |\n|---|---|---|---|---|---|---|---|---|---|---|---|\n")

@@ -510,9 +510,18 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
 
 // ================================================================ dQ ==========
 // CTA = (128-query tile, head pair); 64-key tiles; a thread owns a row and 32 of the 64 columns.
-// smem per head: Q 16K | dO 16K | dS 16K (only used when ATTN_TS bit 1 is off) ; shared: K 3x8K | V 3x8K ; ids ; barriers
-constexpr int DQ_KV_STAGES = 3;
-constexpr int DQP_SMEM = 2 * 49152 + 2 * DQ_KV_STAGES * 8192 + 2 * 2 * 64 * 4 + 2 * 2 * 2 * 4 + 256 + 1024;
+// Round-2 structure: the two heads' tiles form ONE stream of steps v = 2 * tile + head.  Three [S | dP] buffers of 128
+// TMEM columns rotate (buffer v % 3); the bf16 score gradient dS of a step is written OVER the step's own S columns
+// and the dQ MMA reads it there (A operand from tensor memory); tcgen05.mma executes in issue order, so the MMA warp
+// issues the S / dP MMAs of step v + 3 right behind the dQ MMA of step v (same buffer).  The element-wise warps of a
+// head therefore find their next step's S / dP already computed while the other head's step was being worked on,
+// instead of waiting a full hop (dS -> MMA warp -> tensor pipe -> S, dP) every tile with a single buffer per head
+// (round 1: 1.5 us per tile against 0.55 us of compute).  Nothing waits for a dQ MMA to retire except the final read.
+// TMEM columns: [S | dP] x 3 at 0, 128, 256; dQ_h at 384 + 64 h.
+// smem: Q 2x16K | dO 2x16K | K stages x 8K | V stages x 8K | barriers.
+constexpr int DQ_KV_STAGES = 4;
+constexpr int DQP_SMEM = 65536 + 2 * DQ_KV_STAGES * 8192 + 256 + 1024;
+static_assert((ATTN_TS & 6) == 6, "the backward kernels keep dS / Pt / dSt in tensor memory");
 
 template <bool SILU>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
@@ -522,19 +531,15 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
   uint8_t* base = smem_align1024(smem_raw);
   uint8_t* sQ = base;                  // [2][16K]
   uint8_t* sDO = sQ + 32768;           // [2][16K]
-  uint8_t* sDS = sDO + 32768;          // [2][16K]
-  uint8_t* sK = sDS + 32768;           // [stages][8K]
+  uint8_t* sK = sDO + 32768;           // [stages][8K]
   uint8_t* sV = sK + DQ_KV_STAGES * 8192;  // [stages][8K]
-  int32_t* sT = reinterpret_cast<int32_t*>(sV + DQ_KV_STAGES * 8192);  // [2 h][2 st][64]
-  uint32_t* sZ = reinterpret_cast<uint32_t*>(sT + 256);  // [2 h][2 st][2]
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sZ + 8);
-  uint64_t* bar_kv = bar_q + 1;   // [3]
-  uint64_t* bar_s = bar_kv + 3;   // [2] (+2 unused)
-  uint64_t* bar_p = bar_s + 4;    // [2]
-  uint64_t* bar_dq = bar_p + 2;   // [2]
-  uint64_t* bar_dp = bar_dq + 2;  // [2] unused
-  uint64_t* bar_free = bar_dp + 2;  // [3] K/V stage free: both heads' dQ MMAs of the tile it held retired (2 commits)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_free + 3);
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sV + DQ_KV_STAGES * 8192);
+  uint64_t* bar_kv = bar_q + 1;                 // [stages] K / V tile landed
+  uint64_t* bar_free = bar_kv + DQ_KV_STAGES;   // [stages] both heads' dQ MMAs of the tile retired (1 commit, behind head 1's)
+  uint64_t* bar_s = bar_free + DQ_KV_STAGES;    // [3 buffers] S and dP of the step are in the buffer
+  uint64_t* bar_p = bar_s + 3;                  // [3 buffers] dS of the step is written (8 warp arrivals)
+  uint64_t* bar_done = bar_p + 3;               // [2] the head's last dQ MMA retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nqt = p.row_len >> 7;
@@ -549,9 +554,9 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
 
   if (tid == 512) {
     mbar_init(bar_q, 1);
-    for (int i = 0; i < 3; ++i) { mbar_init(&bar_kv[i], 1); mbar_init(&bar_free[i], 2); }
-    for (int i = 0; i < 4; ++i) mbar_init(&bar_s[i], 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_p[i], 8); mbar_init(&bar_dq[i], 1); mbar_init(&bar_dp[i], 1); }
+    for (int i = 0; i < DQ_KV_STAGES; ++i) { mbar_init(&bar_kv[i], 1); mbar_init(&bar_free[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); }
+    for (int i = 0; i < 2; ++i) mbar_init(&bar_done[i], 1);
     fence_barrier_init();
     mbar_expect_tx(bar_q, 65536);  // Q and dO tiles: independent of the segment bounds, requested first
     for (int h = 0; h < 2; ++h) {
@@ -568,14 +573,13 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
   const int kv_lo = p.seg_start[row_base + qt * 128] >> 6;
   const int kv_hi = (p.seg_end[row_base + qt * 128 + 127] + 63) >> 6;
   const int n_kv = kv_hi - kv_lo;
+  const int n_v = 2 * n_kv;   // steps of the stream
 
   if (warp == 16) {
-    // Issue warp.  The whole warp runs the control flow and one elected lane performs the TMA / MMA / barrier side
-    // effects (and the mbarrier polling): descriptors and TMEM addresses are then warp-uniform values held in uniform
-    // registers, which tcgen05.mma reads directly.  A single divergent thread paid two or three R2UR round trips plus
-    // an election retry loop per MMA: ~110 clk per MMA against the 48 clk the tensor pipe needs (N = 64), which made
-    // this warp - 24 MMAs per key tile - the pace-setter of the kernel (timeline: tools/attn_trace_dq.py).
-    const bool leader = elect_one();  // elect.sync-derived: ptxas then knows ONE thread issues and emits back-to-back UTCHMMAs
+    // Issue warp.  The whole warp runs the control flow and one elect.sync-chosen lane performs the MMA / barrier side
+    // effects: descriptors and TMEM addresses are then warp-uniform values held in uniform registers, which tcgen05.mma
+    // reads directly (a lane == 0 compare cost an election retry loop plus R2UR round trips per MMA, ~110 clk each).
+    const bool leader = elect_one();
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
     constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);
     auto wait_u = [&](uint64_t* bar, uint32_t parity) {
@@ -589,74 +593,64 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     // base descriptors; k-steps add 2 (32 B, K-major) or 128 (2048 B, MN-major) to the 16-byte-unit address field
     const uint64_t dQ0 = umma_desc_sw128(smem_u32(sQ), 0, 1024), dQ1 = umma_desc_sw128(smem_u32(sQ + 16384), 0, 1024);
     const uint64_t dO0 = umma_desc_sw128(smem_u32(sDO), 0, 1024), dO1 = umma_desc_sw128(smem_u32(sDO + 16384), 0, 1024);
-    const uint64_t dS0 = umma_desc_sw128(smem_u32(sDS), 0, 1024), dS1 = umma_desc_sw128(smem_u32(sDS + 16384), 0, 1024);
     const uint64_t dKa = umma_desc_sw128(smem_u32(sK), 0, 1024), dVa = umma_desc_sw128(smem_u32(sV), 0, 1024);
     const uint64_t dKt = umma_desc_sw128(smem_u32(sK), 8192, 1024);   // K tile as the MN-major B operand of dQ += dS K
-    (void)dS0; (void)dS1;
-    auto issue_s = [&](int h, int i, uint32_t d, uint64_t* bar) {  // S_h(i) = Q_h K(i)^T
-      const uint64_t dq = h ? dQ1 : dQ0, dk = dKa + (uint64_t)((i % DQ_KV_STAGES) * 512);
-      if (leader) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(d, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
-        if (bar) umma_commit(bar);
+    // S(v) = Q_h K(tile)^T and dP(v) = dO_h V(tile)^T into buffer `buf`; one commit covers both
+    int s_st = 0; uint32_t s_kpar = 0;   // stage / phase of the tile the next S / dP step reads
+    auto issue_sdp = [&](int v, int buf) {
+      const int h = v & 1;
+      if (h == 0) {                       // a new key tile: both heads' steps read it
+        if (v > 0 && ++s_st == DQ_KV_STAGES) { s_st = 0; s_kpar ^= 1; }
+        wait_u(&bar_kv[s_st], s_kpar);
+        tc_fence_after();
       }
-    };
-    auto issue_dp = [&](int h, int i, uint64_t* bar) {  // dP_h(i) = dO_h V(i)^T
-      const uint64_t dd = h ? dO1 : dO0, dv = dVa + (uint64_t)((i % DQ_KV_STAGES) * 512);
+      const uint64_t dq = h ? dQ1 : dQ0, dd = h ? dO1 : dO0;
+      const uint64_t dk = dKa + (uint64_t)(s_st * 512), dv = dVa + (uint64_t)(s_st * 512);
       if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem + h * 192 + 64, dd + 2 * k, dv + 2 * k, idesc_s, k > 0);
-        umma_commit(bar);
-      }
-    };
-    auto issue_dq = [&](int h, int j) {  // dQ_h += dS_h(j) K(j)
-      const uint64_t dk = dKt + (uint64_t)((j % DQ_KV_STAGES) * 512);
-      if (leader) {
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + buf * 128, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-#if ATTN_TS & 2
-          umma_bf16_ts(tmem + h * 192 + 128, tmem + 384 + h * 32 + k * 8, dk + 128 * k, idesc_dq, (j > 0 || k > 0) ? 1u : 0u);
-#else
-          umma_bf16(tmem + h * 192 + 128, (h ? dS1 : dS0) + 2 * k, dk + 128 * k, idesc_dq, (j > 0 || k > 0) ? 1u : 0u);
-#endif
-        umma_commit(&bar_dq[h]);
-        umma_commit(&bar_free[j % DQ_KV_STAGES]);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + buf * 128 + 64, dd + 2 * k, dv + 2 * k, idesc_s, k > 0);
+        umma_commit(&bar_s[buf]);
       }
     };
     wait_u(bar_q, 0);
-    wait_u(&bar_kv[0], 0);
-    tc_fence_after();
-    issue_s(0, 0, tmem, nullptr); issue_dp(0, 0, &bar_s[0]);
-    if (ATTN_STAGGER_B > 0) __nanosleep(ATTN_STAGGER_B);
-    issue_s(1, 0, tmem + 192, nullptr); issue_dp(1, 0, &bar_s[1]);
-    for (int j = 0; j < n_kv; ++j) {
-      // tile j+1 was requested stages ago: check it off before (not after) waiting for dS
-      if (j + 1 < n_kv) wait_u(&bar_kv[(j + 1) % DQ_KV_STAGES], (uint32_t)(((j + 1) / DQ_KV_STAGES) & 1));
-      for (int h = 0; h < 2; ++h) {
-        wait_u(&bar_p[h], j & 1);  // dS_h(j) in smem; S_h/dP_h(j) consumed
-        tc_fence_after();
-        if (leader) ATTN_EVT_DQ(j, h * 2);
-        if (j + 1 < n_kv) {  // next S/dP first: the elementwise warps wait on them, not on dQ
-          issue_s(h, j + 1, tmem + h * 192, nullptr);
-          issue_dp(h, j + 1, &bar_s[h]);   // one commit covers S_h and dP_h
+    for (int v = 0; v < 3 && v < n_v; ++v) issue_sdp(v, v);
+    int buf = 0, q_st = 0;   // buffer of step v; stage of the tile whose dQ MMAs are issued
+    uint32_t ppar = 0;       // phase bits of bar_p per buffer
+    for (int v = 0; v < n_v; ++v) {
+      const int h = v & 1, j = v >> 1;
+      wait_u(&bar_p[buf], (ppar >> buf) & 1u);   // dS(v) is written over the buffer's S columns
+      tc_fence_after();
+      ppar ^= 1u << buf;
+      {
+        // dQ_h += dS(v) K(tile): A = packed dS (columns 0-15: keys 0-31, columns 32-47: keys 32-63 of the buffer)
+        const uint64_t dk = dKt + (uint64_t)(q_st * 512);
+        const uint32_t a0 = tmem + buf * 128;
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ts(tmem + 384 + h * 64, a0 + (k >> 1) * 32 + (k & 1) * 8, dk + 128 * k, idesc_dq, (j > 0 || k > 0) ? 1u : 0u);
+          if (h == 1) umma_commit(&bar_free[q_st]);          // behind both heads' dQ MMAs on the tile
+          if (j == n_kv - 1) umma_commit(&bar_done[h]);
         }
-        issue_dq(h, j);
-        if (leader) ATTN_EVT_DQ(j, h * 2 + 1);
+        if (h == 1 && ++q_st == DQ_KV_STAGES) q_st = 0;
       }
-      if (leader) ATTN_EVT_DQ(j, 4);
+      if (v + 3 < n_v) issue_sdp(v + 3, buf);                 // behind the dQ MMA that read the buffer (issue order)
+      buf = (buf == 2) ? 0 : buf + 1;
     }
   } else if (warp == 17) {
     // Load warp: K/V tiles run up to DQ_KV_STAGES ahead; a stage is refilled as soon as both heads' dQ MMAs of the tile
-    // it held retired.  Kept off the MMA warp on purpose: waiting there for MMA retirement drained the tensor pipe once
-    // per key tile while the next dS sat ready (tools/attn_trace_dq.py: 0.76 us of a 2.1 us step).
+    // it held retired
     if (elect_one()) {
+      int sg = 0; uint32_t fpar = 1; bool first_round = true;
       for (int i = 0; i < n_kv; ++i) {
-        const int sg = i % DQ_KV_STAGES;
-        if (i >= DQ_KV_STAGES) mbar_wait(&bar_free[sg], (uint32_t)((i / DQ_KV_STAGES - 1) & 1));
+        if (!first_round) mbar_wait(&bar_free[sg], fpar);
         const int kr = (int)(row_base + (long long)(kv_lo + i) * 64);
         mbar_expect_tx(&bar_kv[sg], 16384);
         tma_load_2d(sK + sg * 8192, &tmQKV64, &bar_kv[sg], p.k_col + g * 64, kr);
         tma_load_2d(sV + sg * 8192, &tmQKV64, &bar_kv[sg], p.v_col + g * 64, kr);
+        if (++sg == DQ_KV_STAGES) { sg = 0; fpar ^= 1; first_round = false; }
       }
     }
   } else {
@@ -669,9 +663,7 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     const float lse2 = SILU ? 0.f : p.lse2[(long long)h * p.T + tq];
     const float dlt_s = SILU ? 0.f : p.delta[(long long)h * p.T + tq];  // already x 1/8 (attn_delta_kernel)
     const float gs_n = kScale / (float)max(qe - qs, 1);  // SILU: dS = dP * silu'(s/8) / (8 n)
-    const uint32_t t_b = tmem + ((uint32_t)(wq * 32) << 16) + hh * 192;
-    uint8_t* sDSh = sDS + hh * 16384;
-    (void)sDSh;
+    const uint32_t t_lane = tmem + ((uint32_t)(wq * 32) << 16);
 
     // The keys' mask ids come as bitmaps from global memory (graft_token_mask_words), requested one tile ahead: no per-tile
     // staging through shared memory and no head-wide barrier per tile (ncu: that barrier was the kernel's top stall)
@@ -680,6 +672,8 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     uint32_t z_nxt = __ldg(zw), o_nxt = (tmq == 1) ? __ldg(ow) : 0u;
     for (int j = 0; j < n_kv; ++j) {
       const int tile0 = (kv_lo + j) * 64;
+      const int v = 2 * j + hh, buf = v % 3;
+      const uint32_t t_b = t_lane + buf * 128;
       const uint32_t z = z_nxt, o1 = o_nxt;
       if (j + 1 < n_kv) {
         z_nxt = __ldg(zw + 2 * (j + 1));
@@ -692,11 +686,8 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
         w = r & z;
         if (tmq != 0) w |= (tmq == 1) ? (r & o1) : equal_id_word_g(r & ~z, p.tm + row_base + tile0 + half * 32, tmq);
       }
-      mbar_wait(&bar_s[hh], j & 1);
-      if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 6 + hh * 5);
-      if (j > 0) mbar_wait(&bar_dq[hh], (j - 1) & 1);  // dS buffer free
+      mbar_wait(&bar_s[buf], (uint32_t)((v / 3) & 1));
       tc_fence_after();
-      if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 7 + hh * 5);
       uint32_t pk[16];
       if (!__any_sync(0xffffffffu, w != 0u)) {
 #pragma unroll
@@ -705,7 +696,6 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
         float s[32], dp[32];
         tmem_ld_32x32_f(t_b + half * 32, s);
         tmem_ld_32x32_f(t_b + 64 + half * 32, dp);
-        if ((warp & 7) == 0 && lane == 0 && hh == 0) ATTN_EVT_DQ(j, 15);   // x0: both tiles in registers
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
           const uint32_t wb = (w >> (8 * g8)) & 0xffu;
@@ -735,26 +725,17 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
           }
         }
       }
-      if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 8 + hh * 5);
-#if ATTN_TS & 2
-      tmem_st_32x16(tmem + ((uint32_t)(wq * 32) << 16) + 384 + hh * 32 + half * 16, pk);
+      tmem_st_32x16(t_b + half * 32, pk);   // over this thread's own (already read) score columns
       tmem_st_wait();
-#else
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4)
-        *reinterpret_cast<uint4*>(sDSh + sw128_off(t, half * 4 + q4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-      fence_async_smem();
-#endif
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p[hh]);  // one arrival per warp: 8 instead of 256 serialised updates of one mbarrier
-      if ((warp & 7) == 0 && lane == 0) ATTN_EVT_DQ(j, 9 + hh * 5);
+      if (lane == 0) mbar_arrive(&bar_p[buf]);  // one arrival per warp: 8 instead of 256 serialised updates of one mbarrier
     }
-    mbar_wait(&bar_dq[hh], (n_kv - 1) & 1);
+    mbar_wait(&bar_done[hh], 0);
     tc_fence_after();
     __nv_bfloat16* drow = p.dqkv + tq * p.ld + h * 64 + half * 32;
     float v[32];
-    tmem_ld_32x32_f(t_b + 128 + half * 32, v);
+    tmem_ld_32x32_f(t_lane + 384 + hh * 64 + half * 32, v);
     if (p.rope_cos) unrope_row_32(v, p, (int)(tq % p.row_len), half);  // d(q before RoPE): transpose rotation, fused here
     store_row_bf16_32(drow, v, 1.f);
   }
@@ -769,9 +750,13 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
 // ================================================================ dK/dV =======
 // CTA = (128-key tile, kv head); head slot w walks heads g*hpg + w + 2i and their 64-query tiles;
 // a thread owns a key row and 32 of the tile's 64 query columns.
-// smem: K 16K | V 16K | per slot: Q 2x8K, dO 2x8K, Pt 16K, dSt 16K | per-query scalars | barriers
-constexpr int DKV_Q_STAGES = 3;                                   // Q / dO tile stages per head slot
-constexpr int DKV_SLOT = DKV_Q_STAGES * 16384 + 32768;            // per slot: Q [st][8K] | dO [st][8K] | Pt 16K | dSt 16K
+// Same rotating stream as the dQ kernel: step v = 2 * iteration + slot, three [St | dPt] buffers of 128 TMEM columns;
+// Pt is written over the step's St columns, dSt over its dPt columns, and the accumulate MMAs (dV += Pt dO, dK += dSt Q)
+// read them there; the St / dPt MMAs of step v + 3 are issued right behind the accumulate MMAs of step v.
+// TMEM columns: [St | dPt] x 3 at 0, 128, 256; dV at 384, dK at 448.
+// smem: K 16K | V 16K | per slot: Q stages x 8K, dO stages x 8K | per-warp lse / delta slots | barriers
+constexpr int DKV_Q_STAGES = 4;                                   // Q / dO tile stages per head slot
+constexpr int DKV_SLOT = DKV_Q_STAGES * 16384;                    // per slot: Q [st][8K] | dO [st][8K]
 constexpr int DKVP_SMEM = 32768 + 2 * DKV_SLOT + 16 * 128 * 4 + 256 + 1024;
 
 template <bool SILU>
@@ -782,15 +767,15 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
   uint8_t* base = smem_align1024(smem_raw);
   uint8_t* sK = base;
   uint8_t* sV = sK + 16384;
-  uint8_t* sW = sV + 16384;  // per slot: Q [stages][8K] | dO [stages][8K] | Pt 16K | dSt 16K
+  uint8_t* sW = sV + 16384;  // per slot: Q [stages][8K] | dO [stages][8K]
   float* sWarp = reinterpret_cast<float*>(sW + 2 * DKV_SLOT);  // [16 warps][2 buffers][lse 32 | delta 32]
   uint64_t* bar_k = reinterpret_cast<uint64_t*>(sWarp + 16 * 128);
   uint64_t* bar_q = bar_k + 1;     // [2 slot][stages] Q / dO tile landed
   uint64_t* bar_qfree = bar_q + 2 * DKV_Q_STAGES;  // [2 slot][stages] the accumulate MMAs that read the stage retired
-  uint64_t* bar_s = bar_qfree + 2 * DKV_Q_STAGES;  // [2]
-  uint64_t* bar_p = bar_s + 2;     // [2]
-  uint64_t* bar_acc = bar_p + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 2);
+  uint64_t* bar_s = bar_qfree + 2 * DKV_Q_STAGES;  // [3 buffers]
+  uint64_t* bar_p = bar_s + 3;     // [3 buffers]
+  uint64_t* bar_done = bar_p + 3;  // [1] the last accumulate MMAs retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkt = p.row_len >> 7;
@@ -804,7 +789,8 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
   if (tid == 512) {
     mbar_init(bar_k, 1);
     for (int i = 0; i < 2 * DKV_Q_STAGES; ++i) { mbar_init(&bar_q[i], 1); mbar_init(&bar_qfree[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); mbar_init(&bar_acc[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); }
+    mbar_init(bar_done, 1);
     fence_barrier_init();
     mbar_expect_tx(bar_k, 32768);  // this CTA's K and V tiles: requested before the sync / segment loads
     tma_load_2d(sK, &tmQKV128, bar_k, p.k_col + g * 64, (int)(row_base + kt * 128));
@@ -820,6 +806,7 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
   const int q_hi = (p.seg_end[row_base + kt * 128 + 127] + 63) >> 6;
   const int n_q = q_hi - q_lo;
   const int n_it = n_q * (hpg >> 1);
+  const int n_v = 2 * n_it;
 
   if (warp == 16) {
     // MMA issue warp: warp-uniform control flow, all lanes poll, one elect.sync-chosen lane issues (see the dQ kernel)
@@ -835,79 +822,75 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
 #endif
     };
     const uint64_t dKa = umma_desc_sw128(smem_u32(sK), 0, 1024), dVa = umma_desc_sw128(smem_u32(sV), 0, 1024);
-    auto issue_s = [&](int w, int st) {  // St_w = K Q^T, dPt_w = V dO^T
+    // St(v) = K Q^T, dPt(v) = V dO^T of slot v & 1, iteration v >> 1 into buffer `buf`
+    int s_st[2] = {0, 0}; uint32_t s_par[2] = {0, 0};   // per slot: stage / phase of the next Q / dO tile the score MMAs read
+    auto issue_s = [&](int v, int buf) {
+      const int w = v & 1;
+      const int st = w ? s_st[1] : s_st[0];
+      wait_u(&bar_q[w * DKV_Q_STAGES + st], w ? s_par[1] : s_par[0]);
+      tc_fence_after();
       uint8_t* wb = sW + w * DKV_SLOT;
       const uint64_t dq = umma_desc_sw128(smem_u32(wb + st * 8192), 0, 1024);
       const uint64_t dd = umma_desc_sw128(smem_u32(wb + DKV_Q_STAGES * 8192 + st * 8192), 0, 1024);
       if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem + w * 128, dKa + 2 * k, dq + 2 * k, idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + buf * 128, dKa + 2 * k, dq + 2 * k, idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem + w * 128 + 64, dVa + 2 * k, dd + 2 * k, idesc_s, k > 0);
-        umma_commit(&bar_s[w]);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + buf * 128 + 64, dVa + 2 * k, dd + 2 * k, idesc_s, k > 0);
+        umma_commit(&bar_s[buf]);
       }
+      if (w) { if (++s_st[1] == DKV_Q_STAGES) { s_st[1] = 0; s_par[1] ^= 1; } }
+      else   { if (++s_st[0] == DKV_Q_STAGES) { s_st[0] = 0; s_par[0] ^= 1; } }
     };
     wait_u(bar_k, 0);
-    for (int w = 0; w < 2; ++w) {
-      wait_u(&bar_q[w * DKV_Q_STAGES], 0);
+    for (int v = 0; v < 3 && v < n_v; ++v) issue_s(v, v);
+    int buf = 0, a_st = 0;   // buffer of step v; stage of the iteration whose accumulate MMAs are issued
+    uint32_t ppar = 0;
+    for (int v = 0; v < n_v; ++v) {
+      const int w = v & 1;
+      wait_u(&bar_p[buf], (ppar >> buf) & 1u);   // Pt(v) / dSt(v) are written over the buffer's St / dPt columns
       tc_fence_after();
-      if (w == 1 && ATTN_STAGGER_B > 0) __nanosleep(ATTN_STAGGER_B);
-      issue_s(w, 0);
-    }
-    for (int it = 0; it < n_it; ++it) {
-      const int st = it % DKV_Q_STAGES, st1 = (it + 1) % DKV_Q_STAGES;
-      if (it + 1 < n_it) {  // the next Q / dO tiles were requested stages ago: check them off before waiting for Pt
-        wait_u(&bar_q[st1], (uint32_t)(((it + 1) / DKV_Q_STAGES) & 1));
-        wait_u(&bar_q[DKV_Q_STAGES + st1], (uint32_t)(((it + 1) / DKV_Q_STAGES) & 1));
-      }
-      for (int w = 0; w < 2; ++w) {
-        wait_u(&bar_p[w], it & 1);  // Pt_w/dSt_w(it) written; St_w/dPt_w(it) consumed
-        tc_fence_after();
-        if (it + 1 < n_it) issue_s(w, st1);  // next St/dPt first: the elementwise warps wait on them
+      ppar ^= 1u << buf;
+      {
         uint8_t* wb = sW + w * DKV_SLOT;
         // dO / Q tiles as MN-major B operands of the accumulate MMAs (k-step = 16 query rows = 2048 B = 128 units)
-        const uint64_t dq_t = umma_desc_sw128(smem_u32(wb + st * 8192), 8192, 1024);
-        const uint64_t dd_t = umma_desc_sw128(smem_u32(wb + DKV_Q_STAGES * 8192 + st * 8192), 8192, 1024);
-#if !(ATTN_TS & 4)
-        const uint64_t dp = umma_desc_sw128(smem_u32(wb + DKV_Q_STAGES * 16384), 0, 1024);
-        const uint64_t ds = umma_desc_sw128(smem_u32(wb + DKV_Q_STAGES * 16384 + 16384), 0, 1024);
-#endif
-        const uint32_t first = (it == 0 && w == 0) ? 0u : 1u;
+        const uint64_t dq_t = umma_desc_sw128(smem_u32(wb + a_st * 8192), 8192, 1024);
+        const uint64_t dd_t = umma_desc_sw128(smem_u32(wb + DKV_Q_STAGES * 8192 + a_st * 8192), 8192, 1024);
+        const uint32_t first = (v == 0) ? 0u : 1u;
+        const uint32_t a0 = tmem + buf * 128;
         if (leader) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // dV += Pt . dO
-#if ATTN_TS & 4
-            umma_bf16_ts(tmem + 256, tmem + 384 + w * 64 + k * 8, dd_t + 128 * k, idesc_acc, (k > 0) ? 1u : first);
-#else
-            umma_bf16(tmem + 256, dp + 2 * k, dd_t + 128 * k, idesc_acc, (k > 0) ? 1u : first);
-#endif
+            umma_bf16_ts(tmem + 384, a0 + (k >> 1) * 32 + (k & 1) * 8, dd_t + 128 * k, idesc_acc, (k > 0) ? 1u : first);
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // dK += dSt . Q
-#if ATTN_TS & 4
-            umma_bf16_ts(tmem + 320, tmem + 384 + w * 64 + 32 + k * 8, dq_t + 128 * k, idesc_acc, (k > 0) ? 1u : first);
-#else
-            umma_bf16(tmem + 320, ds + 2 * k, dq_t + 128 * k, idesc_acc, (k > 0) ? 1u : first);
-#endif
-          umma_commit(&bar_acc[w]);
-          umma_commit(&bar_qfree[w * DKV_Q_STAGES + st]);
+            umma_bf16_ts(tmem + 448, a0 + 64 + (k >> 1) * 32 + (k & 1) * 8, dq_t + 128 * k, idesc_acc, (k > 0) ? 1u : first);
+          umma_commit(&bar_qfree[w * DKV_Q_STAGES + a_st]);
+          if (v == n_v - 1) umma_commit(bar_done);
         }
+        if (w == 1 && ++a_st == DKV_Q_STAGES) a_st = 0;
       }
+      if (v + 3 < n_v) issue_s(v + 3, buf);   // behind the accumulate MMAs that read the buffer (issue order)
+      buf = (buf == 2) ? 0 : buf + 1;
     }
   } else if (warp == 17) {
     // Load warp: the slots' Q / dO tiles run up to DKV_Q_STAGES iterations ahead of the MMAs
     if (elect_one()) {
+      int st = 0; uint32_t fpar = 1; bool first_round = true;
+      int hi = 0, qi = 0;
       for (int it = 0; it < n_it; ++it) {
-        const int st = it % DKV_Q_STAGES;
-        const int qr = (int)(row_base + (long long)(q_lo + it % n_q) * 64);
+        const int qr = (int)(row_base + (long long)(q_lo + qi) * 64);
         for (int w = 0; w < 2; ++w) {
-          const int h = g * hpg + w + 2 * (it / n_q);
+          const int h = g * hpg + w + 2 * hi;
           uint8_t* wb = sW + w * DKV_SLOT;
           uint64_t* bar = &bar_q[w * DKV_Q_STAGES + st];
-          if (it >= DKV_Q_STAGES) mbar_wait(&bar_qfree[w * DKV_Q_STAGES + st], (uint32_t)((it / DKV_Q_STAGES - 1) & 1));
+          if (!first_round) mbar_wait(&bar_qfree[w * DKV_Q_STAGES + st], fpar);
           mbar_expect_tx(bar, 16384);
           tma_load_2d(wb + st * 8192, &tmQKV64, bar, h * 64, qr);
           tma_load_2d(wb + DKV_Q_STAGES * 8192 + st * 8192, &tmDO64, bar, h * 64, qr);
         }
+        if (++qi == n_q) { qi = 0; ++hi; }
+        if (++st == DKV_Q_STAGES) { st = 0; fpar ^= 1; first_round = false; }
       }
     }
   } else {
@@ -917,11 +900,7 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
     const int tmk = p.tm[tk];
     const int ks = p.seg_start[tk], ke = p.seg_end[tk];
     const float inv_n = 1.f / (float)max(ke - ks, 1);  // a key and the queries that see it share one user run
-    const uint32_t t_b = tmem + ((uint32_t)(wq * 32) << 16) + hh * 128;
-    uint8_t* wb = sW + hh * DKV_SLOT;
-    uint8_t* sPT = wb + DKV_Q_STAGES * 16384;
-    uint8_t* sDST = sPT + 16384;
-    (void)sPT; (void)sDST;
+    const uint32_t t_lane = tmem + ((uint32_t)(wq * 32) << 16);
 
     // Per-query scalars of the tile's 32 query columns (lse, delta) and their mask-id bitmaps are requested ONE TILE AHEAD:
     // lane l fetches column l's lse and delta into a warp-private smem slot (double-buffered), the mask word into a
@@ -929,12 +908,12 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
     // latency in the tile's critical path (reading them where they are used cost +10 %).
     float* sMy = sWarp + warp * 128;   // [2 buffers][lse 32 | delta 32]
     int hi = 0, qi = 0;                // it = hi * n_q + qi without dividing
-    auto fetch = [&](int hi_, int qi_, int buf, uint32_t& mw) {
+    auto fetch = [&](int hi_, int qi_, int sbuf, uint32_t& mw) {
       const int h_ = g * hpg + hh + 2 * hi_;
       const long long q0_ = row_base + (long long)(q_lo + qi_) * 64 + half * 32;
       if (!SILU) {
-        sMy[buf * 64 + lane] = __ldg(p.lse2 + (long long)h_ * p.T + q0_ + lane);
-        sMy[buf * 64 + 32 + lane] = __ldg(p.delta + (long long)h_ * p.T + q0_ + lane);   // already x 1/8
+        sMy[sbuf * 64 + lane] = __ldg(p.lse2 + (long long)h_ * p.T + q0_ + lane);
+        sMy[sbuf * 64 + 32 + lane] = __ldg(p.delta + (long long)h_ * p.T + q0_ + lane);   // already x 1/8
       }
       mw = (tmk == 0) ? 0u : (tmk == 1) ? __ldg(p.one_words + (q0_ >> 5)) : __ldg(p.zero_words + (q0_ >> 5));
     };
@@ -943,6 +922,8 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
     for (int it = 0; it < n_it; ++it) {
       const int tile0 = (q_lo + qi) * 64;
       const long long q0 = row_base + tile0 + half * 32;
+      const int v = 2 * it + hh, buf = v % 3;
+      const uint32_t t_b = t_lane + buf * 128;
       const uint32_t mw = mw_nxt;
       if (++qi == n_q) { qi = 0; ++hi; }
       __syncwarp();                      // this tile's slot was written by the whole warp one iteration ago
@@ -956,8 +937,7 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
       }
       const float4* sl = reinterpret_cast<const float4*>(sMy + (it & 1) * 64);
       const float4* sd = reinterpret_cast<const float4*>(sMy + (it & 1) * 64 + 32);
-      mbar_wait(&bar_s[hh], it & 1);
-      if (it > 0) mbar_wait(&bar_acc[hh], (it - 1) & 1);  // Pt/dSt buffers free
+      mbar_wait(&bar_s[buf], (uint32_t)((v / 3) & 1));
       tc_fence_after();
       uint32_t pp[16], pd[16];
       if (!__any_sync(0xffffffffu, w != 0u)) {
@@ -1000,31 +980,17 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
           }
         }
       }
-#if ATTN_TS & 4
-      {
-        const uint32_t t_a = tmem + ((uint32_t)(wq * 32) << 16) + 384 + hh * 64 + half * 16;
-        tmem_st_32x16(t_a, pp);
-        tmem_st_32x16(t_a + 32, pd);
-        tmem_st_wait();
-      }
-#else
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        const uint32_t off = sw128_off(t, half * 4 + q4);
-        *reinterpret_cast<uint4*>(sPT + off) = make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
-        *reinterpret_cast<uint4*>(sDST + off) = make_uint4(pd[4 * q4], pd[4 * q4 + 1], pd[4 * q4 + 2], pd[4 * q4 + 3]);
-      }
-      fence_async_smem();
-#endif
+      tmem_st_32x16(t_b + half * 32, pp);        // Pt over this thread's own St columns
+      tmem_st_32x16(t_b + 64 + half * 32, pd);   // dSt over its own dPt columns
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p[hh]);  // one arrival per warp: 8 instead of 256 serialised updates of one mbarrier
+      if (lane == 0) mbar_arrive(&bar_p[buf]);  // one arrival per warp: 8 instead of 256 serialised updates of one mbarrier
     }
-    // both slots' accumulate MMAs must have retired; slot 0 stores dV, slot 1 stores dK
-    mbar_wait(&bar_acc[0], (n_it - 1) & 1);
-    mbar_wait(&bar_acc[1], (n_it - 1) & 1);
+    // the accumulate MMAs must have retired; slot 0's warps store dV, slot 1's store dK
+    mbar_wait(bar_done, 0);
     tc_fence_after();
-    const uint32_t t_acc = tmem + ((uint32_t)(wq * 32) << 16) + 256 + hh * 64 + half * 32;
+    const uint32_t t_acc = t_lane + 384 + hh * 64 + half * 32;
     __nv_bfloat16* drow = p.dqkv + tk * p.ld + (hh == 0 ? p.v_col : p.k_col) + g * 64 + half * 32;
     float v[32];
     tmem_ld_32x32_f(t_acc, v);

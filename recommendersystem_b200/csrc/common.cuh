@@ -233,6 +233,16 @@ __device__ __forceinline__ float silu_grad_fast(float x) {
   const float sg = fmaf(0.5f, t, 0.5f);
   return sg * fmaf(x, 1.f - sg, 1.f);
 }
+// backward of act = bf16(silu(gate)) * up for one element (transformer.model.py:212-213 under autocast), `da` = d act (bf16
+// value): d gate = bf16(da * up) * silu'(gate), d up = da * bf16(silu(gate)); one MUFU (tanh) per element.  Shared by the
+// stand-alone kernel and the GEMM epilogue that fuses it, so the two are bit-identical.
+__device__ __forceinline__ void swiglu_bwd_elem(float g, float u, float da, float& dgate, float& dup) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * g));
+  const float sg = fmaf(0.5f, t, 0.5f);
+  dgate = bf16_round(da * u) * (sg * fmaf(g, 1.f - sg, 1.f));
+  dup = da * bf16_round(g * sg);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -239,11 +239,11 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, const __
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     float2 gv = unpack_bf16(gw[k]), uv = unpack_bf16(uw[k]), av = unpack_bf16(aw[k]);
-    float sg0 = 1.f / (1.f + __expf(-gv.x)), sg1 = 1.f / (1.f + __expf(-gv.y));
-    float s0 = gv.x * sg0, s1 = gv.y * sg1;
-    float ds0 = sg0 * (1.f + gv.x * (1.f - sg0)), ds1 = sg1 * (1.f + gv.y * (1.f - sg1));
-    og[k] = pack_bf16(bf16_round(av.x * uv.x) * ds0, bf16_round(av.y * uv.y) * ds1);
-    ou[k] = pack_bf16(av.x * bf16_round(s0), av.y * bf16_round(s1));
+    float dg0, du0, dg1, du1;
+    swiglu_bwd_elem(gv.x, uv.x, av.x, dg0, du0);
+    swiglu_bwd_elem(gv.y, uv.y, av.y, dg1, du1);
+    og[k] = pack_bf16(dg0, dg1);
+    ou[k] = pack_bf16(du0, du1);
   }
   *reinterpret_cast<uint4*>(dgu + t * 2 * I + go) = make_uint4(og[0], og[1], og[2], og[3]);
   *reinterpret_cast<uint4*>(dgu + t * 2 * I + uo) = make_uint4(ou[0], ou[1], ou[2], ou[3]);

@@ -62,7 +62,7 @@ class AttnArgs(C.Structure):
 
 
 (EPI_BF16, EPI_F32, EPI_F32_ACCUM, EPI_RESID, EPI_BIAS_BF16, EPI_BIAS_GELU, EPI_CE_PARTIAL, EPI_CE_GRAD, EPI_TABLE,
- EPI_SWIGLU, EPI_ROPE, EPI_BF16_ACCUM) = range(12)
+ EPI_SWIGLU, EPI_ROPE, EPI_BF16_ACCUM, EPI_SWIGLU_BWD) = range(13)
 
 _lib = None
 
@@ -365,6 +365,30 @@ def swiglu_bwd(gu, dact, dgu, interleaved64=False):
 
 def cast_bf16(src, dst):
     _check(load().graft_cast_f32_to_bf16(ptr(src), ptr(dst), i64(src.numel()), stream()), "graft_cast_f32_to_bf16")
+
+
+class MaskArgs(C.Structure):
+    _fields_ = [("n", i64), ("randval", vp), ("mask_rate", f32), ("finetune_metric", C.c_int),
+                ("token_mask_ids", vp), ("matchedid", vp), ("status", vp), ("rating", vp), ("progress", vp),
+                ("position", vp * 4), ("label", vp * 4), ("weight", vp * 4)]
+
+
+def mask_tokens(d, randval, mask_rate, finetune_metric=None):
+    """transformer.model.py:417-462 on the batch dict's arrays, in place, one launch (dtypes as _normalise_batch leaves them)."""
+    a = MaskArgs()
+    a.n = d["userid"].numel()
+    a.randval = tptr(randval, torch.float32, "randval") if randval is not None else None
+    a.mask_rate = float(mask_rate)
+    a.finetune_metric = -1 if finetune_metric is None else ("watch", "rating").index(finetune_metric)
+    for k in ("token_mask_ids", "matchedid", "status"):
+        setattr(a, k, tptr(d[k], torch.int32, k))
+    a.rating, a.progress = tptr(d["rating"], torch.float32, "rating"), tptr(d["progress"], torch.float32, "progress")
+    for m in (0, 1):
+        for t, metric in enumerate(("watch", "rating")):
+            a.position[2 * m + t] = tptr(d[f"{m}.{metric}.position"], torch.int32, "position").value
+            a.label[2 * m + t] = tptr(d[f"{m}.{metric}.label"], torch.float32, "label").value
+            a.weight[2 * m + t] = tptr(d[f"{m}.{metric}.weight"], torch.float32, "weight").value
+    _check(load().graft_mask_tokens(C.byref(a), stream()), "graft_mask_tokens")
 
 
 class CastJob(C.Structure):

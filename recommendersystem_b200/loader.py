@@ -158,3 +158,45 @@ def write_shards(datadir, per_user, n_shards, users_per_file, batch_size, seed=0
                 d["userid"] = np.full(len(d["userid"]), i + 1, np.int32)
                 chunk[i] = d
             np.savez(os.path.join(dest, f"{p + 1}.npz"), **packer.concat(chunk, batch_size))
+
+
+class FinetuneDataset:
+    """Mirror of the reference's FinetuneDataset + collate + to_device (transformer.py:101-184) for the finetune step: files
+    hold [users, max_seq_len] matrices (Finetune/transformer.jl:135-166); only users with a target of the finetuned medium
+    are kept (:136-143); training takes every `checkpoints_per_epoch`-th such user of the current partition, shuffles them and
+    pads the list to a multiple of batch_size by re-drawing (:144-152); batches are dicts of [batch_size, max_seq_len]
+    tensors, `.position` as int64 on the device (:179-183).  The row filter is one vectorised reduction instead of the
+    reference's Python loop over users; iteration order and draws follow the reference (np.random, as seeded by the caller)."""
+
+    def __init__(self, datadir, local_rank, local_world_size, batch_size, shuffle, finetune_medium, device=None, checkpoints_per_epoch=4):
+        self.batch_size, self.shuffle, self.medium = int(batch_size), bool(shuffle), int(finetune_medium)
+        shards = sorted(glob.glob(os.path.join(datadir, "*", "")))
+        self.fns = []
+        for s in packer.shards_for_rank(shards, local_rank, local_world_size):
+            self.fns.extend(glob.glob(os.path.join(s, "*.h5")) + glob.glob(os.path.join(s, "*.npz")))
+        self.partition = [0, checkpoints_per_epoch]
+        self.device = torch.device(device) if device is not None else None
+
+    def rows_with_targets(self, d):
+        """transformer.py:136-143: users whose finetuned medium has a watch or rating weight."""
+        w = d[f"{self.medium}.watch.weight"].sum(axis=1) > 0
+        r = d[f"{self.medium}.rating.weight"].sum(axis=1) > 0
+        return np.flatnonzero(w | r).tolist()
+
+    def __iter__(self):
+        for fn in self.fns:
+            d = read_shard_file(fn)
+            idxs = self.rows_with_targets(d)
+            if self.shuffle:
+                idxs = [x for i, x in enumerate(idxs) if i % self.partition[1] == self.partition[0]]
+                np.random.shuffle(idxs)
+                while len(idxs) % self.batch_size != 0:
+                    idxs.append(np.random.choice(idxs))
+            for i in range(0, len(idxs), self.batch_size):
+                idx = idxs[i: i + self.batch_size]
+                batch = {k: torch.as_tensor(np.ascontiguousarray(v[idx, :])) for k, v in d.items()}
+                if self.device is not None:
+                    batch = {k: (v.pin_memory() if self.device.type == "cuda" else v).to(self.device, non_blocking=True) for k, v in batch.items()}
+                    batch = {k: (v.to(torch.int64) if k.endswith(".position") else v) for k, v in batch.items()}
+                yield batch
+        self.partition[0] = (self.partition[0] + 1) % self.partition[1]

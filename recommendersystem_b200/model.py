@@ -362,6 +362,22 @@ def _f32(shape, dev):
     return torch.empty(shape, dtype=torch.float32, device=dev)
 
 
+def _block_weights_bf16(wq_, wk_, wv_, wo_, w1_, w3_, w2_, H, G, dm, I, dev, with_o_t=False):
+    """bf16 operand copies of one block's weights in ONE launch (graft_cast_jobs): fused [q; k; v], Wo (+ its transpose for
+    the backward), w1 / w3 interleaved in 64-row blocks (one GEMM tile then holds matching gate and up columns and the SwiGLU
+    product is formed in its epilogue), w2."""
+    QKV = (H + 2 * G) * 64
+    qkv_w = _bf16((QKV, dm), dev); o_w = _bf16((dm, H * 64), dev); w13 = _bf16((2 * I, dm), dev); w2 = _bf16((dm, I), dev)
+    o_t = _bf16((H * 64, dm), dev) if with_o_t else None
+    det = lambda t: t.detach().contiguous()
+    jobs = [(det(wq_), qkv_w, L.CAST_PLAIN, 0), (det(wk_), qkv_w, L.CAST_PLAIN, H * 64), (det(wv_), qkv_w, L.CAST_PLAIN, (H + G) * 64),
+            (det(wo_), o_w, L.CAST_PLAIN, 0), (det(w1_), w13, L.CAST_GATE64, 0), (det(w3_), w13, L.CAST_UP64, 0), (det(w2_), w2, L.CAST_PLAIN, 0)]
+    if with_o_t:
+        jobs.append((det(wo_), o_t, L.CAST_TRANSPOSE, 0))
+    L.cast_jobs(jobs)
+    return qkv_w, o_w, w13, w2, o_t
+
+
 class _ClozeStep(torch.autograd.Function):
     """Whole step as one autograd node: forward returns the loss vector, backward
     consumes d(loss vector) (a device tensor, no host sync) and returns every
@@ -392,20 +408,11 @@ class _ClozeStep(torch.autograd.Function):
         Vt = V0 + cfg["vocab_sizes"]["1_matchedid"]
         sv = {}  # saved for backward
 
-        # ---- bf16 operand copies of the weights (autocast's casts, done once per step) ----
+        # ---- bf16 operand copies of the weights (autocast's casts, done once per step): one launch per block ----
         wq = []
         for i in range(nl):
-            qkv_w = _bf16((QKV, dm), dev)
-            L.cast_bf16(W[f"l{i}.q"], qkv_w[: H * 64]); L.cast_bf16(W[f"l{i}.k"], qkv_w[H * 64:(H + G) * 64])
-            L.cast_bf16(W[f"l{i}.v"], qkv_w[(H + G) * 64:])
-            o_w = _bf16((dm, H * 64), dev); L.cast_bf16(W[f"l{i}.o"], o_w)
-            # gate/up rows interleaved in 64-row blocks so one GEMM tile holds matching gate and up
-            # columns and the SwiGLU product is formed in its epilogue
-            w13 = _bf16((2 * I, dm), dev)
-            w13v = w13.view(I // 64, 2, 64, dm)
-            w13v[:, 0].copy_(W[f"l{i}.w1"].detach().view(I // 64, 64, dm)); w13v[:, 1].copy_(W[f"l{i}.w3"].detach().view(I // 64, 64, dm))
-            w2 = _bf16((dm, I), dev); L.cast_bf16(W[f"l{i}.w2"], w2)
-            wq.append((qkv_w, o_w, w13, w2))
+            wq.append(_block_weights_bf16(W[f"l{i}.q"], W[f"l{i}.k"], W[f"l{i}.v"], W[f"l{i}.o"], W[f"l{i}.w1"], W[f"l{i}.w3"],
+                                          W[f"l{i}.w2"], H, G, dm, I, dev, with_o_t=True))
         sv["wq"] = wq
         lw = []
         if P.lora:
@@ -449,7 +456,7 @@ class _ClozeStep(torch.autograd.Function):
         layers = []
         dlt = None  # bf16 output of the previous block's w2 GEMM: its residual add rides on the next norm
         for i in range(nl):
-            qkv_w, o_w, w13, w2 = wq[i]
+            qkv_w, o_w, w13, w2, _o_t = wq[i]
             xn = _bf16((T, dm), dev); r1 = _f32((T,), dev)
             if dlt is None:
                 L.rmsnorm_fwd(x, W[f"l{i}.san"], xn, None, r1)
@@ -551,16 +558,17 @@ class _ClozeStep(torch.autograd.Function):
                             out[2 * m:2 * m + 1])
                 vp = dict(hs_all=hs_all, pos_loc=pos_loc, s0=s0, s1=s1)
             # rating: Linear -> GELU -> Linear(d,1), weighted MSE / moments
-            rsel, rws, rlab, _rpos, _rc = L.select_rows(d[f"{m}.rating.weight"].reshape(-1), d[f"{m}.rating.label"].reshape(-1),
-                                                        d[f"{m}.rating.position"].reshape(-1).to(torch.int32), cap)
+            rsel, rws, rlab, _rpos, rcnt = L.select_rows(d[f"{m}.rating.weight"].reshape(-1), d[f"{m}.rating.label"].reshape(-1),
+                                                         d[f"{m}.rating.position"].reshape(-1).to(torch.int32), cap)
             rhs = _bf16((cap, dm), dev); L.gather_rows_bf16(hidden, rsel, 1, rhs)
-            h1 = _bf16((cap, dm), dev); pre = _bf16((cap, dm), dev)
-            L.gemm(rhs, w0_16, h1, cap, dm, dm, epilogue=L.EPI_BIAS_GELU, bias=W["rh.b0"], aux=pre)
+            # only the row blocks that hold rating targets are computed (device-side limit); the rest stays zero
+            h1 = torch.zeros((cap, dm), dtype=torch.bfloat16, device=dev); pre = torch.zeros((cap, dm), dtype=torch.bfloat16, device=dev)
+            L.gemm(rhs, w0_16, h1, cap, dm, dm, epilogue=L.EPI_BIAS_GELU, bias=W["rh.b0"], aux=pre, m_count=rcnt)
             pred = _f32((cap,), dev)
             loss4 = out[4 + 4 * m: 8 + 4 * m]
             L.rating_tail(h1, W["rh.w2"], W["rh.b2"], rlab, rws, cfg["rating_mean"], pred, loss4)
             heads.append(dict(lo=lo, hi=hi, sel=sel, hs=hs, pos=pos, lse=lse_r, coef=coef, cnt=cnt, vp=vp, rsel=rsel, rhs=rhs, h1=h1, pre=pre,
-                              pred=pred, rlab=rlab, rws=rws))
+                              pred=pred, rlab=rlab, rws=rws, rcnt=rcnt))
         out[1] = out[4]  # train MSE = first moment
         out[3] = out[8]
         sv["heads"], sv["out"] = heads, out
@@ -596,7 +604,10 @@ class _ClozeStep(torch.autograd.Function):
             dtable[Vt].zero_()  # rows [0,Vt) are fully written by the head GEMMs below
         dhid = torch.zeros((T, dm), dtype=torch.float32, device=dev)
         table16 = sv["table16"]
-        CH = 4096
+        # catalog columns per backward chunk of the cloze head: 16384 columns x the ~19 live row blocks = ~1200 tiles for the
+        # logit-gradient GEMM (8 waves) and 384 tiles for d table; round 1's 4096-column chunks left every launch
+        # wave-quantised (57 tiles on 148 SMs for d hidden) and cost 69 launches per step
+        CH = 16384
         dw0 = _f32((dm, dm), dev); db0 = torch.zeros(dm, dtype=torch.float32, device=dev)
         dw2 = torch.zeros(dm, dtype=torch.float32, device=dev); db2 = torch.zeros(1, dtype=torch.float32, device=dev)
         tmp_dw2 = _f32((dm,), dev); tmp_db2 = _f32((1,), dev); tmp_db0 = _f32((dm,), dev)
@@ -623,8 +634,9 @@ class _ClozeStep(torch.autograd.Function):
                 L.gemm(hs_rows, items, dlog, rows_n, cn, dm, ldc=CH, epilogue=L.EPI_CE_GRAD,
                        ce=dict(lse=lse_rows, coef=coef_rows, target=tgt_rows), n_offset=c0, m_count=lim)
                 # d hidden rows += dlogits . items
+                # (only ~19 of the 64 row blocks are live: five K splits give the 57 live tiles ~285 work units = 1.93 waves on 148 SMs)
                 L.gemm(dlog, items, dhs, rows_n, dm, cn, lda=CH, b_kmajor=False, ldb=dm,
-                       epilogue=L.EPI_F32 if c0 == 0 else L.EPI_F32_ACCUM, m_count=lim)
+                       epilogue=L.EPI_F32 if c0 == 0 else L.EPI_F32_ACCUM, m_count=lim, split_k=5 if cn >= 4096 else 0)
                 # d table rows = dlogits^T . hidden rows
                 if tab:
                     L.gemm(dlog, hs_rows, dtable[c_lo + c0: c_lo + c0 + cn], cn, dm, rows_n, a_kmajor=False, lda=CH,
@@ -640,10 +652,10 @@ class _ClozeStep(torch.autograd.Function):
             if base:
                 dw2 += tmp_dw2; db2 += tmp_db2
                 L.gemm(dpre, hd["rhs"], dw0, dm, dm, cap, a_kmajor=False, lda=dm, b_kmajor=False, ldb=dm,
-                       epilogue=L.EPI_F32 if m == 0 else L.EPI_F32_ACCUM, split_k=-1)
+                       epilogue=L.EPI_F32 if m == 0 else L.EPI_F32_ACCUM, split_k=-1, k_count=hd["rcnt"])
                 L.colsum(dpre, tmp_db0); db0 += tmp_db0
             drhs = _f32((cap, dm), dev)
-            L.gemm(dpre, sv["w0_16"], drhs, cap, dm, dm, b_kmajor=False, ldb=dm, epilogue=L.EPI_F32)
+            L.gemm(dpre, sv["w0_16"], drhs, cap, dm, dm, b_kmajor=False, ldb=dm, epilogue=L.EPI_F32, m_count=hd["rcnt"])
             L.scatter_rows_f32(drhs, hd["rsel"], 1, dhid)
         G_["rh.w0"], G_["rh.b0"], G_["rh.w2"], G_["rh.b2"] = dw0, db0, dw2.reshape(1, dm), db2
 
@@ -658,16 +670,14 @@ class _ClozeStep(torch.autograd.Function):
 
         for i in reversed(range(nl)):
             x, xn, r1, qkv, ao, lse, h, hn, r2, gu, act, lora = sv["layers"][i]
-            qkv_w, o_w, w13, w2 = sv["wq"][i]
-            # x_out = h + act . W2^T
-            dact = _bf16((T, I), dev)
-            L.gemm(dx16, w2, dact, T, I, dm, b_kmajor=False, ldb=I)
+            qkv_w, o_w, w13, w2, o_t = sv["wq"][i]
+            # x_out = h + act . W2^T.  d(act) = dx . W2 and the SwiGLU backward in one kernel: the GEMM's epilogue reads the
+            # gate / up tiles of `gu` and writes d(gate | up); d(act) itself never reaches HBM
+            dgu = _bf16((T, 2 * I), dev)
+            L.gemm(dx16, w2, dgu, T, I, dm, b_kmajor=False, ldb=I, ldc=2 * I, epilogue=L.EPI_SWIGLU_BWD, aux=gu, ldaux=2 * I)
             if base:
                 g_w2 = _f32((dm, I), dev)
                 L.gemm(dx16, act, g_w2, dm, I, T, a_kmajor=False, lda=dm, b_kmajor=False, ldb=I, epilogue=L.EPI_F32, split_k=-1)
-            dgu = _bf16((T, 2 * I), dev)
-            L.swiglu_bwd(gu, dact, dgu, interleaved64=True)
-            del dact
             dhn = _bf16((T, dm), dev)
             L.gemm(dgu, w13, dhn, T, dm, 2 * I, b_kmajor=False, ldb=dm)
             if base:
@@ -679,7 +689,8 @@ class _ClozeStep(torch.autograd.Function):
             L.rmsnorm_bwd(h, W[f"l{i}.mln"], r2, dhn, None, dx, dh, dh16, g_mln)
             # h = x + ao . Wo^T
             dao = _bf16((T, H * 64), dev)
-            L.gemm(dh16, o_w, dao, T, H * 64, dm, b_kmajor=False, ldb=H * 64)
+            # against a transposed copy of Wo (K-major B): the MN-major form of this 768-deep shape ran at 39 % of peak
+            L.gemm(dh16, o_t, dao, T, H * 64, dm)
             if base:
                 g_o = _f32((dm, H * 64), dev)
                 L.gemm(dh16, ao, g_o, dm, H * 64, T, a_kmajor=False, lda=dm, b_kmajor=False, ldb=H * 64, epilogue=L.EPI_F32,
@@ -900,7 +911,6 @@ class RecommenderModel(nn.Module):
         QKV = (H + 2 * G) * 64
         layers = []
         for i in range(cfg["num_layers"]):
-            qkv_w = _bf16((QKV, dm), dev)
             wq_, wv_ = W[f"l{i}.q"].detach(), W[f"l{i}.v"].detach()
             if P.lora:
                 # inference has no dropout, so the LoRA branch (ref:263-271) is a rank-8 update of the weight:
@@ -908,13 +918,8 @@ class RecommenderModel(nn.Module):
                 # the difference is bf16 rounding noise, inside the 1e-2 tolerance)
                 wq_ = wq_ + 2.0 * (W[f"l{i}.qB"].detach() @ W[f"l{i}.qA"].detach())
                 wv_ = wv_ + 2.0 * (W[f"l{i}.vB"].detach() @ W[f"l{i}.vA"].detach())
-            L.cast_bf16(wq_.contiguous(), qkv_w[: H * 64]); L.cast_bf16(W[f"l{i}.k"], qkv_w[H * 64:(H + G) * 64])
-            L.cast_bf16(wv_.contiguous(), qkv_w[(H + G) * 64:])
-            o_w = _bf16((dm, H * 64), dev); L.cast_bf16(W[f"l{i}.o"], o_w)
-            w13 = _bf16((2 * I, dm), dev)
-            w13v = w13.view(I // 64, 2, 64, dm)
-            w13v[:, 0].copy_(W[f"l{i}.w1"].detach().view(I // 64, 64, dm)); w13v[:, 1].copy_(W[f"l{i}.w3"].detach().view(I // 64, 64, dm))
-            w2 = _bf16((dm, I), dev); L.cast_bf16(W[f"l{i}.w2"], w2)
+            qkv_w, o_w, w13, w2, _ = _block_weights_bf16(wq_, W[f"l{i}.k"], wv_, W[f"l{i}.o"], W[f"l{i}.w1"], W[f"l{i}.w3"],
+                                                        W[f"l{i}.w2"], H, G, dm, I, dev)
             layers.append((qkv_w, o_w, w13, w2))
         table = self.item_embedding.table()
         w0_16 = _bf16((dm, dm), dev); L.cast_bf16(W["rh.w0"], w0_16)
@@ -978,41 +983,19 @@ class RecommenderModel(nn.Module):
         return pred.view(U, T2, 1).to(torch.bfloat16)
 
     def mask_tokens(self, d):
-        """ref:417-462 (pre-train branch): same draws, same in-place edits of `d`."""
+        """ref:417-462: same draw (torch.rand, so a seeded run masks the same positions as the reference) and the same
+        in-place edits of `d`, applied by one graft_mask_tokens launch instead of ~30 boolean-index assignments."""
         shape, dev = d["userid"].shape, d["userid"].device
+        for k in d:  # the kernel edits the arrays in place: they must be the dict's own dense storage
+            if not d[k].is_contiguous():
+                d[k] = d[k].contiguous()
         if self.config["finetune"]:  # ref:418-435: the held-out targets of the finetuned metric are the masked positions
             pick = self.config["finetune_metric"]
             assert pick in ALL_METRICS
-            hit = torch.zeros(shape, dtype=torch.bool, device=dev)
-            for k in d:
-                if pick in k and k.endswith(".weight"):
-                    hit |= d[k] > 0
-            none = torch.zeros_like(hit)
-            watch, rating = (hit, none) if pick == "watch" else (none, hit)
+            L.mask_tokens(d, None, 0.0, finetune_metric=pick)
         else:
             randval = self.mask_rand(shape, dev) if self.mask_rand is not None else torch.rand(shape, device=dev)
-            rate = self.config["mask_rate"]
-            watch = randval < rate
-            rating = (randval >= rate) & (randval < 2 * rate)
-        either = watch | rating
-        not_watch, not_rating = ~watch, ~rating
-        d["token_mask_ids"] *= rating
-        for k in d:  # masked_fill_ = the reference's boolean index assignment without its host sync
-            if k.endswith(".position") or k.endswith(".label") or k.endswith(".weight"):
-                if "watch" in k:
-                    d[k].masked_fill_(not_watch, 0)
-                elif "rating" in k:
-                    d[k].masked_fill_(not_rating, 0)
-                elif "status" not in k:
-                    raise AssertionError(k)
-            elif k == "matchedid":
-                d[k].masked_fill_(watch, -1)
-            elif k == "status":
-                d[k].masked_fill_(either, -1)
-            elif k in ("rating", "progress"):
-                d[k].masked_fill_(either, 0)
-            elif k not in ("userid", "token_mask_ids", "time", "gender", "source"):
-                raise AssertionError(k)
+            L.mask_tokens(d, randval.to(torch.float32).contiguous(), self.config["mask_rate"])
         return d
 
     @torch.compiler.disable
@@ -1021,6 +1004,8 @@ class RecommenderModel(nn.Module):
         if not self.config["finetune"]:
             for k in d:
                 d[k] = d[k].reshape(-1, S)  # ref:495-496 (mutates the caller's dict, as the trainer expects)
+        if not d["userid"].is_cuda or not self.rating_head[0].weight.is_cuda:
+            raise L.GraftError("the cloze step has no CPU path: move the model and batch to a CUDA device")
         _normalise_batch(d)
         d = self.mask_tokens(d)
         for k in d:

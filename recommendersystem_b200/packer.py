@@ -76,6 +76,76 @@ def _columns(items):
                 h_status=opt("history_status"), h_rating=opt("history_rating"))
 
 
+def _tokenize_project(items):
+    """`tokenize!` (collapse runs of one (medium, matchedid): first event's fields, last event's status / rating /
+    progress) then `project!` (drop events that change neither status nor rating), history_tools.jl:37-75, on columns."""
+    c = _columns(items)
+    n0 = len(c["medium"])
+    if n0:
+        key = c["medium"].astype(np.int64) << 32 | c["matchedid"].astype(np.int64)
+        start = np.flatnonzero(np.r_[True, key[1:] != key[:-1]])       # first event of each span
+        last = np.r_[start[1:], n0] - 1                                 # last event of each span
+    else:
+        start = last = np.zeros(0, np.int64)
+    out = dict(medium=c["medium"][start], matchedid=c["matchedid"][start], ts=c["ts"][start], h_status=c["h_status"][start],
+               h_rating=c["h_rating"][start], status=c["status"][last], rating=c["rating"][last], progress=c["progress"][last])
+    keep = ~((out["h_status"] == out["status"]) & (out["h_rating"] == out["rating"]))   # NaN (nothing) never equals: kept
+    return {k: v[keep] for k, v in out.items()}
+
+
+def _targets(c):
+    """Watch / rating / status target hits of a token column set: transformer.jl:120-140 (= Finetune/transformer.jl:104-121)."""
+    no_hist = np.isnan(c["h_status"])
+    status, rating = c["status"], c["rating"]
+    watch = ((status == 0) & no_hist) | ((status > PLANNED_STATUS) & (no_hist | ((c["h_status"] > 0) & (c["h_status"] <= PLANNED_STATUS))))
+    rated = (rating > 0) & ~(rating == c["h_rating"])
+    stat = (status > 0) & ~(status == c["h_status"])
+    return {"watch": watch, "rating": rated, "status": stat}
+
+
+def get_data_finetune(data, userid, num_items0, max_seq_len=1024, num_test_items=1):
+    """Finetune packer row, /root/reference/notebooks/Finetune/transformer.jl:52-133: the user's tokenized + projected history
+    (last max_seq_len - num_test_items tokens) followed by the held-out test items in one zero-padded row of max_seq_len
+    positions; only the test items carry targets, and every (medium, metric) weight vector is normalised to sum 1.
+    Returns the 27 arrays of length max_seq_len (one row of the [users, max_seq_len] matrices FinetuneDataset reads)."""
+    assert len(data["test_items"]) <= num_test_items
+    h = _tokenize_project(data["items"])
+    keep = max_seq_len - num_test_items
+    if len(h["medium"]) > keep:
+        h = {k: v[len(v) - keep:] for k, v in h.items()}
+    t = _columns(data["test_items"])
+    nh, nt = len(h["medium"]), len(t["medium"])
+    n = nh + nt
+    cat = {k: np.concatenate([h[k], t[k]]) for k in h}
+    u = data["user"]
+    N = max_seq_len
+
+    def row(values, dtype):
+        out = np.zeros(N, dtype)
+        out[:n] = values
+        return out
+
+    d = {"userid": row(userid, np.int32), "token_mask_ids": np.zeros(N, np.int32), "time": row(cat["ts"], np.float64),
+         "gender": row(0 if u["gender"] is None else u["gender"] + 1, np.int32), "source": row(u["source"], np.int32),
+         "matchedid": row(cat["matchedid"] + np.where(cat["medium"] == 1, num_items0, 0), np.int32),
+         "status": row(cat["status"], np.int32), "rating": row(cat["rating"], np.float32), "progress": row(cat["progress"], np.float32)}
+    hits = _targets(cat)
+    is_test = np.r_[np.zeros(nh, bool), np.ones(nt, bool)]
+    labels = {"watch": np.ones(n, np.float32), "rating": cat["rating"].astype(np.float32), "status": cat["status"].astype(np.float32)}
+    d["token_mask_ids"] = row((hits["rating"] & is_test).astype(np.int32), np.int32)
+    for m in (0, 1):
+        for metric in PACK_METRICS:
+            hit = hits[metric] & is_test & (cat["medium"] == m)
+            w = hit.astype(np.float32)
+            wsum = w.sum(dtype=np.float32)
+            if wsum > 0:
+                w = w / wsum
+            d[f"{m}.{metric}.label"] = row(np.where(hit, labels[metric], 0), np.float32)
+            d[f"{m}.{metric}.weight"] = row(w, np.float32)
+            d[f"{m}.{metric}.position"] = row(np.where(hit, cat["matchedid"], 0), np.int32)
+    return d
+
+
 def get_data(data, userid, num_items0):
     """Columnar restatement of the Julia packer's per-user step: `tokenize!` (collapse runs of
     one (medium, matchedid): first event's fields, last event's status/rating/progress),

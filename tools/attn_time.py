@@ -18,7 +18,12 @@ T, QKV = 2 * rows * S, (H + 2 * G) * 64
 batch = synthetic.make_batches(cfg, rows, 1, seed=1000)[0]
 g = torch.Generator(device=dev).manual_seed(0)
 qkv = (torch.randn((T, QKV), device=dev, generator=g) * 0.5).bfloat16()
-tm = torch.zeros(T, dtype=torch.int32, device=dev)
+# mask ids as a training step has them after mask_tokens (transformer.model.py:441): 1 on ~10 % of the positions (both tokens
+# of the position), 0 elsewhere; ATTN_TM=0 gives the all-zero ids of the first-round measurements
+if os.environ.get("ATTN_TM", "1") == "0":
+    tm = torch.zeros(T, dtype=torch.int32, device=dev)
+else:
+    tm = (torch.rand(T // 2, device=dev, generator=g) < 0.1).to(torch.int32).repeat_interleave(2).contiguous()
 ao = torch.empty((T, H * 64), dtype=torch.bfloat16, device=dev); lse = torch.empty((H, T), device=dev)
 dao = torch.randn((T, H * 64), device=dev, generator=g).bfloat16(); dqkv = torch.empty_like(qkv); delta = torch.empty((H, T), device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
