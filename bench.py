@@ -176,7 +176,11 @@ def gpu_bench(args):
     model = RecommenderModel(cfg)
     model.load_pretrained_embeddings(metadata=synthetic.make_metadata(cfg))
     model = model.to(dev)
-    opt = FlatAdamW(model, lr=cfg["learning_rate"])
+    gcomm = None
+    if world > 1 and args.graft_comm:  # the gradient all-reduce through the C ABI (graft_allreduce_f32, library-owned NCCL communicator)
+        from recommendersystem_b200.comm import GraftComm
+        gcomm = GraftComm(device=local)
+    opt = FlatAdamW(model, lr=cfg["learning_rate"], graft_comm=gcomm)
     tw = make_task_weights(finetune_metric="rating") if args.config == "C3" else make_task_weights()
     S = cfg["max_sequence_length"]
     n_inter = rows * S
@@ -200,6 +204,8 @@ def gpu_bench(args):
         return torch.stack([l.detach() for l in losses])
 
     graphed = None
+    if cfg.get("vocab_parallel") and world > 1:
+        args.no_graph = True   # the vocab-parallel head exchanges rows through NCCL inside the step: launched eagerly, not captured
     if not args.no_graph:
         try:
             graphed = GraphedStep(model, tw, resident[0])
@@ -347,6 +353,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-table", default=None, help="write a per-shape table of the GEMM launches (markdown) to this path")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--graft-comm", action="store_true", help="N > 1: all-reduce the gradient with graft_allreduce_f32 instead of torch.distributed")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
 

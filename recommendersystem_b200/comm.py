@@ -80,3 +80,44 @@ def all_to_all_rows(t, group=None):
     dist.all_gather(parts, host, group=group)
     r = rank(group)
     return torch.stack([p[r] for p in parts]).to(t.device)
+
+
+class GraftComm:
+    """Library-owned NCCL communicator (include/graft.h: graft_comm_*): the data-parallel all-reduce of the flat gradient
+    buffer issued through the C ABI on any stream.  Rank 0 draws the NCCL unique id; it reaches the other ranks through the
+    already initialised torch.distributed group (any backend)."""
+
+    def __init__(self, device=None, group=None):
+        import ctypes as C
+        from . import lib as L
+        self._lib = L.load()
+        self.rank, self.world = rank(group), world(group)
+        if device is not None:
+            torch.cuda.set_device(device)
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            L._check(self._lib.graft_comm_unique_id(buf), "graft_comm_unique_id")
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        if self.world > 1:
+            on_gpu = dist.get_backend(group) == "nccl"
+            t = ident.cuda() if on_gpu else ident
+            dist.broadcast(t, src=0, group=group)
+            ident = t.cpu()
+        raw = (C.c_ubyte * 128)(*ident.tolist())
+        self._comm = C.c_void_p()
+        L._check(self._lib.graft_comm_create(raw, self.rank, self.world, C.byref(self._comm)), "graft_comm_create")
+
+    def all_reduce_(self, t, stream=None):
+        """In-place SUM over the ranks of a contiguous fp32 CUDA tensor, stream-ordered on `stream` (default: current)."""
+        import ctypes as C
+        from . import lib as L
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        st = L.stream() if stream is None else L.vp(stream.cuda_stream)
+        L._check(self._lib.graft_allreduce_f32(self._comm, L.vp(t.data_ptr()), C.c_int64(t.numel()), st), "graft_allreduce_f32")
+        return t
+
+    def close(self):
+        if self._comm:
+            self._lib.graft_comm_destroy(self._comm)
+            self._comm = None

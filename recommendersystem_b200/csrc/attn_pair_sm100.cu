@@ -962,16 +962,20 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
               const float gn = kScale * inv_n;
               g0 = silu_grad_fast(z0) * dp[c] * gn; g1 = silu_grad_fast(z1) * dp[c + 1] * gn;
               g2 = silu_grad_fast(z2) * dp[c + 2] * gn; g3 = silu_grad_fast(z3) * dp[c + 3] * gn;
+              if (!clean) {
+                const bool b0 = (w >> c) & 1u, b1 = (w >> (c + 1)) & 1u, b2 = (w >> (c + 2)) & 1u, b3 = (w >> (c + 3)) & 1u;
+                p0 = b0 ? p0 : 0.f; p1 = b1 ? p1 : 0.f; p2 = b2 ? p2 : 0.f; p3 = b3 ? p3 : 0.f;
+                g0 = b0 ? g0 : 0.f; g1 = b1 ? g1 : 0.f; g2 = b2 ? g2 : 0.f; g3 = b3 ? g3 : 0.f;
+              }
             } else {
               p0 = ex2(fmaf(s[c], kScaleLog2, -l4.x)); p1 = ex2(fmaf(s[c + 1], kScaleLog2, -l4.y));
               p2 = ex2(fmaf(s[c + 2], kScaleLog2, -l4.z)); p3 = ex2(fmaf(s[c + 3], kScaleLog2, -l4.w));
+              if (!clean) {  // one select per element: the score gradient is a multiple of the masked probability
+                p0 = (w >> c) & 1u ? p0 : 0.f; p1 = (w >> (c + 1)) & 1u ? p1 : 0.f;
+                p2 = (w >> (c + 2)) & 1u ? p2 : 0.f; p3 = (w >> (c + 3)) & 1u ? p3 : 0.f;
+              }
               g0 = p0 * fmaf(dp[c], kScale, -d4.x); g1 = p1 * fmaf(dp[c + 1], kScale, -d4.y);
               g2 = p2 * fmaf(dp[c + 2], kScale, -d4.z); g3 = p3 * fmaf(dp[c + 3], kScale, -d4.w);
-            }
-            if (!clean) {
-              const bool b0 = (w >> c) & 1u, b1 = (w >> (c + 1)) & 1u, b2 = (w >> (c + 2)) & 1u, b3 = (w >> (c + 3)) & 1u;
-              p0 = b0 ? p0 : 0.f; p1 = b1 ? p1 : 0.f; p2 = b2 ? p2 : 0.f; p3 = b3 ? p3 : 0.f;
-              g0 = b0 ? g0 : 0.f; g1 = b1 ? g1 : 0.f; g2 = b2 ? g2 : 0.f; g3 = b3 ? g3 : 0.f;
             }
             pp[c >> 1] = pack_bf16(p0, p1);
             pp[(c >> 1) + 1] = pack_bf16(p2, p3);

@@ -76,7 +76,7 @@ _LAUNCHES_PER_CALL = {
     "graft_jagged_offsets": 2, "graft_action_embed": 2, "graft_action_embed_bwd": 5, "graft_scatter_add_sorted": 6,
     "graft_rmsnorm_bwd": 2, "graft_colsum": 2, "graft_attn_bwd": 3, "graft_ce_finish": 2, "graft_rating_tail": 2,
     "graft_rating_tail_bwd": 3, "graft_sumsq_f32": 2, "graft_jagged_offsets_host": 0, "graft_block_permutation_host": 0,
-    "graft_concat_pad_host": 0, "graft_status_flags": 0,
+    "graft_concat_pad_host": 0, "graft_status_flags": 0, "graft_comm_unique_id": 0, "graft_comm_create": 0,
 }
 
 
@@ -553,6 +553,67 @@ def scale_by_scalar(v, scalar):
 
 def interleave_i32(a, out):
     _check(load().graft_interleave_i32(tptr(a, torch.int32, "token_mask_ids"), i64(a.numel()), ptr(out), stream()), "graft_interleave_i32")
+
+
+# ----------------------------------------------------------------- fp32 mode --
+def gemm_f32(A, B, Cout, M, N, K, *, a_t=False, b_nk=True, lda=None, ldb=None, ldc=None, accumulate=False, bias=None, m_count=None):
+    """C[M,N] (+)= op(A) op(B) (+ bias): A [M,K] ([K,M] when a_t), B [N,K] when b_nk (a Linear weight) else [K,N]; all fp32."""
+    for t in (A, B, Cout):
+        assert t.dtype == torch.float32
+    lda = lda if lda is not None else (M if a_t else K)
+    ldb = ldb if ldb is not None else (K if b_nk else N)
+    ldc = ldc if ldc is not None else N
+    _check(load().graft_gemm_f32(vp(A.data_ptr()), i64(lda), int(a_t), vp(B.data_ptr()), i64(ldb), int(b_nk), vp(Cout.data_ptr()), i64(ldc),
+                                 i64(M), i64(N), i64(K), int(accumulate), ptr(bias), ptr(m_count), stream()), "graft_gemm_f32")
+
+
+def attn_f32_fwd(qkv, H, G, rows, row_len, tm_tok, seg_s, seg_e, out, lse):
+    _check(load().graft_attn_f32_fwd(ptr(qkv), i64(qkv.shape[1]), H, G, rows, row_len, ptr(tm_tok), ptr(seg_s), ptr(seg_e), ptr(out), ptr(lse),
+                                     stream()), "graft_attn_f32_fwd")
+
+
+def attn_f32_bwd(qkv, H, G, rows, row_len, tm_tok, seg_s, seg_e, out, dout, lse, dqkv, delta):
+    _check(load().graft_attn_f32_bwd(ptr(qkv), i64(qkv.shape[1]), H, G, rows, row_len, ptr(tm_tok), ptr(seg_s), ptr(seg_e), ptr(out), ptr(dout),
+                                     ptr(lse), ptr(dqkv), ptr(delta), stream()), "graft_attn_f32_bwd")
+
+
+def rope_f32(x, heads, row_len, cos, sin, inverse=False):
+    _check(load().graft_rope_f32(ptr(x), i64(x.shape[0]), i64(x.shape[1]), heads, row_len, ptr(cos), ptr(sin), int(inverse), stream()), "graft_rope_f32")
+
+
+def swiglu_f32_fwd(gu, act):
+    _check(load().graft_swiglu_f32_fwd(ptr(gu), ptr(act), i64(act.shape[0]), act.shape[1], stream()), "graft_swiglu_f32_fwd")
+
+
+def swiglu_f32_bwd(gu, dact, dgu):
+    _check(load().graft_swiglu_f32_bwd(ptr(gu), ptr(dact), ptr(dgu), i64(dact.shape[0]), dact.shape[1], stream()), "graft_swiglu_f32_bwd")
+
+
+def gelu_f32(x, out, dy=None):
+    _check(load().graft_gelu_f32(ptr(x), ptr(dy), ptr(out), i64(x.numel()), stream()), "graft_gelu_f32")
+
+
+def gather_rows_f32(x, sel, parity, out):
+    _check(load().graft_gather_rows_f32(ptr(x), x.shape[1], ptr(sel), sel.numel(), parity, ptr(out), stream()), "graft_gather_rows_f32")
+
+
+def ce_rows_f32(logits, K, target, pmax, psum, tgt):
+    _check(load().graft_ce_rows_f32(ptr(logits), i64(logits.shape[1]), logits.shape[0], K, ptr(target), ptr(pmax), ptr(psum), ptr(tgt), stream()),
+           "graft_ce_rows_f32")
+
+
+def ce_grad_f32(logits, K, target, lse, coef):
+    _check(load().graft_ce_grad_f32(ptr(logits), i64(logits.shape[1]), logits.shape[0], K, ptr(target), ptr(lse), ptr(coef), stream()),
+           "graft_ce_grad_f32")
+
+
+def rating_moments_f32(pred, lab, w, mean, loss4):
+    _check(load().graft_rating_moments_f32(ptr(pred), ptr(lab), ptr(w), pred.numel(), f32(mean), ptr(loss4), stream()), "graft_rating_moments_f32")
+
+
+def rating_dpred_f32(pred, lab, w, mean, loss4, gscale, dp):
+    _check(load().graft_rating_dpred_f32(ptr(pred), ptr(lab), ptr(w), pred.numel(), f32(mean), ptr(loss4), vp(gscale.data_ptr()), ptr(dp), stream()),
+           "graft_rating_dpred_f32")
 
 
 # ---------------------------------------------------------------- optimiser --

@@ -1011,7 +1011,11 @@ class RecommenderModel(nn.Module):
         for k in d:
             if not d[k].is_contiguous():
                 d[k] = d[k].contiguous()
-        res = _ClozeStep.apply(self, d, bool(evaluate), *self._params.tensors)
+        if self.config.get("precision", "bf16") == "fp32":   # the step without autocast: fp32 kernels, parity 1e-4 (model_fp32.py)
+            from .model_fp32 import ClozeStepF32
+            res = ClozeStepF32.apply(self, d, bool(evaluate), *self._params.tensors)
+        else:
+            res = _ClozeStep.apply(self, d, bool(evaluate), *self._params.tensors)
         if evaluate:
             res, mom = res
             return [res[0], [mom[0, 0], mom[0, 1], mom[0, 2]], res[2], [mom[1, 0], mom[1, 1], mom[1, 2]]]

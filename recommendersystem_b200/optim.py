@@ -51,7 +51,10 @@ def wsd_lr_factor(step, warmup_steps, total_steps, decay_ratio=0.1, final_ratio=
 
 
 class FlatAdamW:
-    def __init__(self, model, lr=1e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1, max_grad_norm=1.0):
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1, max_grad_norm=1.0, graft_comm=None):
+        """graft_comm: a comm.GraftComm -> the gradient all-reduce goes through the C ABI (graft_allreduce_f32, the library's
+        own NCCL communicator) instead of torch.distributed."""
+        self.graft_comm = graft_comm
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
         decay = [(n, p) for n, p in named if p.dim() >= 2]      # transformer.py:288-289
         nodecay = [(n, p) for n, p in named if p.dim() < 2]
@@ -86,7 +89,10 @@ class FlatAdamW:
         buckets).  The sum is reduced; the 1/world of DDP's mean is folded into the clip scale
         that AdamW applies anyway, so no extra pass over the buffer is made."""
         if self.world > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+            if self.graft_comm is not None:
+                self.graft_comm.all_reduce_(self.flat_g)
+            else:
+                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
 
     def clip_scale(self, sumsq):
         """Scale applied to the (summed) gradient: DDP mean x clip_grad_norm_(max_norm)

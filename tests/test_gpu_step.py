@@ -59,6 +59,72 @@ def test_golden_losses_and_grads(golden):
     assert not bad, bad
 
 
+def test_fp32_mode_matches_reference_fp32(golden):
+    """config["precision"] = "fp32" (the step without autocast, model_fp32.py) against the reference's own fp32 run
+    (tests/golden/cloze_tiny.npz `losses`, `grad`): the north star's fp32 tolerance, 1e-4 relative, on every loss and every
+    gradient leaf (relative L2 per leaf), no noise-floor rule."""
+    g = dict(golden, config=dict(golden["config"], precision="fp32"))
+    losses, grads, d = run_golden_step(g, DEV)
+    got = np.array([float(x) for x in losses])
+    print("fp32 losses", got, "reference fp32", golden["losses"])
+    np.testing.assert_allclose(got, golden["losses"], rtol=1e-4)
+    for k, ref in golden["masked"].items():
+        assert np.array_equal(d[k].reshape(-1).cpu().numpy(), ref), k
+    rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+    table = [(rel(grads[k], ref32), 0.0, 0.0, k) for k, ref32 in golden["grad"].items()]
+    worst = max(table)
+    print("fp32 mode: worst gradient leaf", worst[3], worst[0])
+    _write_grad_table("fp32_mode_golden", [(e, e, 0.0, k) for e, _, _, k in table], "fp32 mode vs the reference's fp32 run: relative L2 per leaf (bound 1e-4)")
+    for e, _, _, k in table:
+        assert e < 1e-4, (k, e)
+    out, _, _ = run_golden_step(g, DEV, evaluate=True)
+    flat = []
+    for e in out:
+        flat += [float(x) for x in e] if isinstance(e, list) else [float(e)]
+    np.testing.assert_allclose(flat, golden["eval_flat"], rtol=1e-4)
+
+
+def test_fp32_mode_c1_matches_oracle_fp32():
+    """BASELINE configs[0] (C1: 8 x 256, d 256, 2 blocks, 24 k catalog) in fp32 against the oracle in fp32 on the same GPU
+    inputs: losses and every gradient leaf within 1e-4."""
+    from oracle import cloze_oracle as oc
+    from recommendersystem_b200.model import RecommenderModel
+    from recommendersystem_b200.synthetic import make_batches, make_config, make_metadata
+    cfg, rows = make_config("C1", precision="fp32")
+    torch.manual_seed(5)
+    model = RecommenderModel(cfg)
+    model.load_pretrained_embeddings(metadata=make_metadata(cfg))
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.requires_grad and (n.endswith("bias") or "periodic" in n):
+                p.add_(torch.randn_like(p) * 0.02)
+    model = model.to(DEV)
+    S = cfg["max_sequence_length"]
+    rv = torch.rand((rows, S), generator=torch.Generator().manual_seed(6)).to(DEV)
+    model.mask_rand = lambda shape, dev: rv.reshape(shape)
+    batch = make_batches(cfg, rows, 1, seed=8)[0]
+    tw = oc.default_task_weights()
+    losses = model(batch_to_device(batch, DEV), False)
+    sum(l * w for l, w in zip(losses, tw)).backward()
+    p = {k: v.detach() for k, v in model.state_dict().items() if not k.startswith("watch_head.")}
+    ref_l, ref_g, _ = oc.step_with_grads(batch_to_device(batch, DEV), p, cfg, rv, tw, autocast=False)
+    got = np.array([float(x) for x in losses]); ref = np.array([float(x) for x in ref_l])
+    print("C1 fp32 losses", got, "oracle fp32", ref)
+    np.testing.assert_allclose(got, ref, rtol=1e-4)
+    worst = (0.0, "")
+    for n, q in model.named_parameters():
+        if not q.requires_grad:
+            continue
+        a, b = q.grad.float(), ref_g[n].float()
+        if float(b.norm()) == 0.0:
+            assert float(a.norm()) == 0.0, n
+            continue
+        e = float((a - b).norm() / b.norm())
+        worst = max(worst, (e, n))
+        assert e < 1e-4, (n, e)
+    print("C1 fp32: worst gradient leaf", worst)
+
+
 def test_golden_eval_moments(golden):
     out, _, _ = run_golden_step(golden, DEV, evaluate=True)
     flat = []
