@@ -47,6 +47,25 @@ constexpr int PAIR_THREADS = 576;  // 16 softmax warps, MMA issue warp (16), TMA
 #ifndef ATTN_STAGGER_B
 #define ATTN_STAGGER_B 0
 #endif
+// ATTN_POLY = n > 0: in the forward kernel's unmasked path every n-th pair of exponentials is evaluated on the FMA pipe
+// (Cody-Waite split + degree-3 polynomial, rel. error 6e-4 << bf16's 4e-3) instead of the MUFU: the exp passes are MUFU-bound
+// (16 lanes per SM), the FMA pipe idles.  0 = off.
+#ifndef ATTN_POLY
+#define ATTN_POLY 0
+#endif
+// ATTN_ARRIVAL_ORDER: the forward kernel's issue warp serves whichever head delivered its probabilities first
+#ifndef ATTN_ARRIVAL_ORDER
+#define ATTN_ARRIVAL_ORDER 0
+#endif
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;            // 1.5 * 2^23: the integer nearest to x lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);      // in [-0.5, 0.5]
+  float p = fmaf(f, 0.0555041087f, 0.2402265070f);
+  p = fmaf(p, f, 0.6931471806f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ unsigned int g_attn_work[4];  // work-item counters of the persistent kernels (zeroed before each launch)
 #ifdef ATTN_TRACE  /* diagnostic build: CTA 0 timestamps the events of its first 48 stream tiles (tools/attn_trace.py) */
 __device__ long long g_attn_trace[48 * 16];
@@ -305,6 +324,23 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
           const bool last1 = more_here ? (j + 2 == cur.n_kv) : (nxt.n_kv == 1);
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
+#if ATTN_ARRIVAL_ORDER
+            // serve the heads in the order their probabilities arrive (a fixed order made the head that finished first wait
+            // for the other one's exp pass before its next scores were even issued)
+            uint32_t pending = 3u, spins = 0;
+            while (pending) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                if (!((pending >> h) & 1u)) continue;
+                if (!__all_sync(0xffffffffu, mbar_test(&bar_p[h * 2 + sub], (uint32_t)(g & 1)))) continue;
+                tc_fence_after();
+                issue_pv(h, sub, st, j > 0 || sub > 0, !more_here);
+                if (next_s) issue_s(h, sub, qb1, st1, last1);
+                pending &= ~(1u << h);
+              }
+              if (++spins > (1u << 26)) { printf("graft: attention issue warp timeout block %d\n", blockIdx.x); __trap(); }
+            }
+#else
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               wait_u(&bar_p[h * 2 + sub], (uint32_t)(g & 1));  // P_h(g, sub) is in TMEM (over the S columns it came from)
@@ -312,6 +348,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
               issue_pv(h, sub, st, j > 0 || sub > 0, !more_here);
               if (next_s) issue_s(h, sub, qb1, st1, last1);     // behind the P.V that read these columns (issue order)
             }
+#endif
           }
         }
         cur = nxt;
@@ -451,8 +488,14 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p,
               if (__all_sync(0xffffffffu, w == 0xffffffffu)) {
 #pragma unroll
                 for (int c = 0; c < 32; c += 2) {
-                  const float p0 = SILU ? silu_fast(s[c] * kScale) * inv_n : ex2(fmaf(s[c], kScaleLog2, -mscaled));
-                  const float p1 = SILU ? silu_fast(s[c + 1] * kScale) * inv_n : ex2(fmaf(s[c + 1], kScaleLog2, -mscaled));
+                  float p0, p1;
+                  if (SILU) {
+                    p0 = silu_fast(s[c] * kScale) * inv_n; p1 = silu_fast(s[c + 1] * kScale) * inv_n;
+                  } else if (ATTN_POLY > 0 && ((c >> 1) % (ATTN_POLY > 0 ? ATTN_POLY : 1)) == 0) {
+                    p0 = ex2_poly(fmaf(s[c], kScaleLog2, -mscaled)); p1 = ex2_poly(fmaf(s[c + 1], kScaleLog2, -mscaled));
+                  } else {
+                    p0 = ex2(fmaf(s[c], kScaleLog2, -mscaled)); p1 = ex2(fmaf(s[c + 1], kScaleLog2, -mscaled));
+                  }
                   pk[c >> 1] = pack_bf16(p0, p1);
                 }
               } else {
