@@ -131,3 +131,37 @@ def test_exec_model_file_defines_reference_names_and_refuses_cpu():
         model.item_embedding(torch.arange(0, 4))
     with pytest.raises(L.GraftError):
         model.watch_head((torch.zeros(2, cfg["embed_dim"]), 0))
+
+
+def test_scratch_scope_owned_by_graph_refuses_to_grow():
+    """a captured CUDA graph bakes in workspace pointers; its scope must not hand them back to the allocator.
+    A frozen scope raises instead of replacing a buffer; the default scope keeps growing independently."""
+    import torch
+    scope = L.ScratchScope()
+    with scope:
+        a = L.scratch(1 << 10, "cpu", slot=7)
+        assert L.scratch(1 << 9, "cpu", slot=7) is a          # reused
+    scope.frozen = True
+    with scope:
+        assert L.scratch(1 << 10, "cpu", slot=7) is a
+        with pytest.raises(L.GraftError):
+            L.scratch(8 << 20, "cpu", slot=7)                  # growth after capture
+    b = L.scratch(8 << 20, "cpu", slot=7)                      # the process-wide scope is unaffected
+    assert b is not a and scope.bufs[("cpu", 7)] is a
+    assert isinstance(b, torch.Tensor)
+
+
+def test_batch_dtype_normalisation_in_place():
+    """the kernels hard-code int32 ids / float64 time / float32 values; the reference indexes with any integer
+    dtype, so the drop-in converts instead of reinterpreting (the caller's dict is updated in place, like the mask edits)."""
+    import torch
+    from recommendersystem_b200.model import _normalise_batch
+    d = {"userid": torch.arange(4), "time": torch.ones(4, dtype=torch.float32), "rating": torch.ones(4, dtype=torch.float64),
+         "0.watch.position": torch.arange(4), "0.watch.weight": torch.ones(4, dtype=torch.float64), "matchedid": torch.arange(4, dtype=torch.int32)}
+    keep = d["matchedid"]
+    out = _normalise_batch(d)
+    assert out is d and d["matchedid"] is keep                 # already right: untouched
+    assert d["userid"].dtype == torch.int32 and d["time"].dtype == torch.float64 and d["rating"].dtype == torch.float32
+    assert d["0.watch.position"].dtype == torch.int32 and d["0.watch.weight"].dtype == torch.float32
+    with pytest.raises(L.GraftError):
+        L.tptr(torch.arange(4), torch.int32, "ids")

@@ -289,6 +289,19 @@ def test_c2_shape_oracle_parity():
     torch.cuda.empty_cache()
 
 
+def test_production_shape_oracle_parity():
+    """The reference's production model shape (transformer.py:535-545: d 2048, 32/16 heads, FFN 5632, 8 blocks, S 1024) on 2
+    rows against the oracle under bf16 autocast: the kernels' tile / split heuristics and the 2048-wide norms at the shape
+    the reference actually trains."""
+    from oracle.cloze_oracle import default_task_weights
+    from recommendersystem_b200.synthetic import make_batches, make_config
+    cfg, _ = make_config("P")
+    rows = 2
+    batch = make_batches(cfg, rows, 1, seed=13)[0]
+    _oracle_vs_cuda(cfg, rows, batch, default_task_weights(), seed=12, name="production_shape")
+    torch.cuda.empty_cache()
+
+
 def test_c2_full_size_properties():
     """BASELINE configs[1] at full size (64 x 1024, d=768, 8 blocks, 100k catalog): size-independent
     properties - init watch loss = ln(K_m); padding positions get zero item-table gradient beyond what the

@@ -142,13 +142,15 @@ def main():
         pairs += int(((2 * ls) ** 2).sum())
     attn_flops = 4.0 * H * 64 * pairs
     qkv = (torch.randn((T, QKV), device=dev, generator=g) * 0.5).bfloat16()
-    tm = torch.zeros(T, dtype=torch.int32, device=dev)
+    # mask ids as a training step has them after mask_tokens (id 1 on ~10 % of the positions; round 1 timed all-zero ids,
+    # which skips the per-element select path of every 8-column group that holds a masked key)
+    tm = (torch.rand(T // 2, device=dev, generator=g) < 0.1).to(torch.int32).repeat_interleave(2).contiguous()
     seg_s, seg_e = L.token_segments(uid)
     at = L.attn_args(qkv, H, G, rows, 2 * S, tm, seg_s, seg_e)
     ao = torch.empty((T, H * 64), dtype=torch.bfloat16, device=dev)
     lse = torch.empty((H, T), device=dev)
     ms = timer(lambda: L.attn_fwd(at, ao, lse))
-    rec("attention fwd (jagged, GQA pair)", ms, flops=attn_flops, note=f"sum l_tok^2={pairs} ({pairs / (rows * (2 * S) ** 2):.2f} of dense)")
+    rec("attention fwd (jagged, GQA pair)", ms, flops=attn_flops, note=f"sum l_tok^2={pairs} ({pairs / (rows * (2 * S) ** 2):.2f} of dense); mask id 1 on 10 % of the positions")
     dao = torch.randn((T, H * 64), device=dev, generator=g).bfloat16()
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((H, T), device=dev)
@@ -193,6 +195,15 @@ def main():
     ms = timer(lambda: L.gemm(A, Wq, qkv_f, T, QKV, d, epilogue=L.EPI_ROPE, rope=dict(cos=cost, sin=sint, t_stride=2 * S, cols=(H + G) * 64, row_len=2 * S)))
     rec("gemm qkv proj + fused RoPE epilogue, transposed tables (step path)", ms, flops=2.0 * T * QKV * d, note=f"{T}x{QKV}x{d}")
     del A, Wg, gu_f, act_f, Wq, qkv_f
+    # d(act) = dx . W2 with the SwiGLU backward fused into the epilogue (reads gu, writes dgu; d(act) stays on chip)
+    dxa = (torch.randn((T, d), device=dev, generator=g) * 0.5).bfloat16()
+    w2m = (torch.randn((d, I), device=dev, generator=g) * 0.05).bfloat16()
+    guu = torch.randn((T, 2 * I), device=dev, generator=g).bfloat16()
+    dguu = torch.empty_like(guu)
+    ms = timer(lambda: L.gemm(dxa, w2m, dguu, T, I, d, b_kmajor=False, ldb=I, ldc=2 * I, epilogue=L.EPI_SWIGLU_BWD, aux=guu, ldaux=2 * I))
+    rec("gemm d(act) + fused SwiGLU backward epilogue", ms, flops=2.0 * T * I * d,
+        note=f"{T}x{I}x{d}; also HBM-heavy: {(2 * T * 2 * I * 2 + T * d * 2) / (ms * 1e-3) / 1e9:.0f} GB/s of gu + dgu + dx")
+    del dxa, w2m, guu, dguu
     gemm_case("gemm w2 (down)", T, d, I)
     gemm_case("gemm out proj", T, d, H * 64)
     # dW shape: [2I, T] x [T, d], MN-major operands, split-K
@@ -213,6 +224,11 @@ def main():
     ms = timer(lambda: L.gemm(hs, tab16, None, cap, V0, d, epilogue=L.EPI_CE_PARTIAL, ce=dict(pmax=pmax, psum=psum, tgt=tgt, target=pos)))
     rec("catalog logits + fused CE fwd", ms, flops=2.0 * cap * V0 * d, note=f"{cap} rows x {V0} items; logits never stored "
         f"(would be {cap * V0 * 2 / 1e9:.2f} GB bf16)")
+    lse_r = torch.full((cap,), 11.0, device=dev); coef = torch.full((cap,), 1e-3, device=dev)
+    CHK = 16384
+    dlog = torch.empty((cap, CHK), dtype=torch.bfloat16, device=dev)
+    ms = timer(lambda: L.gemm(hs, tab16[:CHK], dlog, cap, CHK, d, ldc=CHK, epilogue=L.EPI_CE_GRAD, ce=dict(lse=lse_r, coef=coef, target=pos)))
+    rec("catalog logit gradient chunk (CE_GRAD epilogue)", ms, flops=2.0 * cap * CHK * d, note=f"{cap} rows x {CHK} items, all rows live")
 
     # ---------------------------------------------------------------- optimiser (HBM) ----
     n = 135_000_000
