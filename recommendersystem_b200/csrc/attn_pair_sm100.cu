@@ -713,9 +713,10 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
     const uint32_t* zw = p.zero_words + ((row_base + (long long)kv_lo * 64 + half * 32) >> 5);   // + 2 per 64-key tile
     const uint32_t* ow = p.one_words + ((row_base + (long long)kv_lo * 64 + half * 32) >> 5);
     uint32_t z_nxt = __ldg(zw), o_nxt = (tmq == 1) ? __ldg(ow) : 0u;
+    // step v = 2 j + hh uses buffer v % 3 in phase (v / 3) & 1: both are carried along instead of divided out per tile
+    int buf = hh; uint32_t spar = 0u;
     for (int j = 0; j < n_kv; ++j) {
       const int tile0 = (kv_lo + j) * 64;
-      const int v = 2 * j + hh, buf = v % 3;
       const uint32_t t_b = t_lane + buf * 128;
       const uint32_t z = z_nxt, o1 = o_nxt;
       if (j + 1 < n_kv) {
@@ -729,13 +730,16 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
         w = r & z;
         if (tmq != 0) w |= (tmq == 1) ? (r & o1) : equal_id_word_g(r & ~z, p.tm + row_base + tile0 + half * 32, tmq);
       }
-      mbar_wait(&bar_s[buf], (uint32_t)((v / 3) & 1));
+      mbar_wait(&bar_s[buf], spar);
       tc_fence_after();
-      uint32_t pk[16];
+      // each path issues its own store (no zero-initialised registers merged into the working path)
       if (!__any_sync(0xffffffffu, w != 0u)) {
+        uint32_t zr[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) pk[q] = 0u;
+        for (int q = 0; q < 16; ++q) zr[q] = 0u;
+        tmem_st_32x16(t_b + half * 32, zr);
       } else {
+        uint32_t pk[16];
         float s[32], dp[32];
         tmem_ld_32x32_f(t_b + half * 32, s);
         tmem_ld_32x32_f(t_b + 64 + half * 32, dp);
@@ -767,12 +771,13 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
             }
           }
         }
+        tmem_st_32x16(t_b + half * 32, pk);   // over this thread's own (already read) score columns
       }
-      tmem_st_32x16(t_b + half * 32, pk);   // over this thread's own (already read) score columns
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_p[buf]);  // one arrival per warp: 8 instead of 256 serialised updates of one mbarrier
+      if (buf == 0) buf = 2; else { --buf; spar ^= 1u; }   // v += 2
     }
     mbar_wait(&bar_done[hh], 0);
     tc_fence_after();
@@ -950,43 +955,52 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
     // register.  No head-wide barrier per tile (ncu: ~19 % of this kernel's samples sat on it), and no global-memory
     // latency in the tile's critical path (reading them where they are used cost +10 %).
     float* sMy = sWarp + warp * 128;   // [2 buffers][lse 32 | delta 32]
-    int hi = 0, qi = 0;                // it = hi * n_q + qi without dividing
-    auto fetch = [&](int hi_, int qi_, int sbuf, uint32_t& mw) {
-      const int h_ = g * hpg + hh + 2 * hi_;
-      const long long q0_ = row_base + (long long)(q_lo + qi_) * 64 + half * 32;
+    // cursors of the NEXT tile to fetch: query tiles fastest, then the slot's next head (two heads on); plain pointer
+    // increments per tile (ncu: the 64-bit index arithmetic of this prefetch was ~8 % of the kernel's instructions)
+    const long long q_first = row_base + (long long)q_lo * 64 + half * 32;
+    const long long head_step = 2 * p.T - (long long)(n_q - 1) * 64;
+    const float* lse_n = p.lse2 + (long long)(g * hpg + hh) * p.T + q_first + lane;
+    const float* del_n = p.delta + (long long)(g * hpg + hh) * p.T + q_first + lane;   // already x 1/8
+    const uint32_t* mw_n = ((tmk == 1) ? p.one_words : p.zero_words) + (q_first >> 5);
+    int qi_n = 0;
+    auto fetch = [&](int sbuf, uint32_t& mw) {
       if (!SILU) {
-        sMy[sbuf * 64 + lane] = __ldg(p.lse2 + (long long)h_ * p.T + q0_ + lane);
-        sMy[sbuf * 64 + 32 + lane] = __ldg(p.delta + (long long)h_ * p.T + q0_ + lane);   // already x 1/8
+        sMy[sbuf * 64 + lane] = __ldg(lse_n);
+        sMy[sbuf * 64 + 32 + lane] = __ldg(del_n);
       }
-      mw = (tmk == 0) ? 0u : (tmk == 1) ? __ldg(p.one_words + (q0_ >> 5)) : __ldg(p.zero_words + (q0_ >> 5));
+      mw = (tmk == 0) ? 0u : __ldg(mw_n);
+      if (++qi_n == n_q) { qi_n = 0; lse_n += head_step; del_n += head_step; mw_n -= 2 * (n_q - 1); }
+      else { lse_n += 64; del_n += 64; mw_n += 2; }
     };
     uint32_t mw_nxt = 0;
-    if (n_it > 0) fetch(0, 0, 0, mw_nxt);
+    if (n_it > 0) fetch(0, mw_nxt);
+    int qi = 0, tile0 = q_lo * 64;
+    int buf = hh; uint32_t spar = 0u;   // step v = 2 it + hh: buffer v % 3, phase (v / 3) & 1, carried along
     for (int it = 0; it < n_it; ++it) {
-      const int tile0 = (q_lo + qi) * 64;
-      const long long q0 = row_base + tile0 + half * 32;
-      const int v = 2 * it + hh, buf = v % 3;
       const uint32_t t_b = t_lane + buf * 128;
       const uint32_t mw = mw_nxt;
-      if (++qi == n_q) { qi = 0; ++hi; }
       __syncwarp();                      // this tile's slot was written by the whole warp one iteration ago
-      if (it + 1 < n_it) fetch(hi, qi, (it + 1) & 1, mw_nxt);
+      if (it + 1 < n_it) fetch((it + 1) & 1, mw_nxt);
       uint32_t w;
       {
         const uint32_t r = range_word(ks - tile0, ke - tile0, half);
         if (tmk == 0) w = r;                 // a key with mask id 0 is visible to its whole run
         else if (tmk == 1) w = r & mw;       // else only to queries with the same id
-        else w = equal_id_word_g(r & ~mw, p.tm + q0, tmk);
+        else w = equal_id_word_g(r & ~mw, p.tm + row_base + tile0 + half * 32, tmk);
       }
       const float4* sl = reinterpret_cast<const float4*>(sMy + (it & 1) * 64);
       const float4* sd = reinterpret_cast<const float4*>(sMy + (it & 1) * 64 + 32);
-      mbar_wait(&bar_s[buf], (uint32_t)((v / 3) & 1));
+      mbar_wait(&bar_s[buf], spar);
       tc_fence_after();
-      uint32_t pp[16], pd[16];
+      // each path issues its own stores (no zero-initialised registers merged into the working path)
       if (!__any_sync(0xffffffffu, w != 0u)) {
+        uint32_t zr[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) { pp[q] = 0u; pd[q] = 0u; }
+        for (int q = 0; q < 16; ++q) zr[q] = 0u;
+        tmem_st_32x16(t_b + half * 32, zr);
+        tmem_st_32x16(t_b + 64 + half * 32, zr);
       } else {
+        uint32_t pp[16], pd[16];
         float s[32], dp[32];
         tmem_ld_32x32_f(t_b + half * 32, s);
         tmem_ld_32x32_f(t_b + 64 + half * 32, dp);
@@ -1011,12 +1025,17 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
                 g0 = b0 ? g0 : 0.f; g1 = b1 ? g1 : 0.f; g2 = b2 ? g2 : 0.f; g3 = b3 ? g3 : 0.f;
               }
             } else {
-              p0 = ex2(fmaf(s[c], kScaleLog2, -l4.x)); p1 = ex2(fmaf(s[c + 1], kScaleLog2, -l4.y));
-              p2 = ex2(fmaf(s[c + 2], kScaleLog2, -l4.z)); p3 = ex2(fmaf(s[c + 3], kScaleLog2, -l4.w));
-              if (!clean) {  // one select per element: the score gradient is a multiple of the masked probability
-                p0 = (w >> c) & 1u ? p0 : 0.f; p1 = (w >> (c + 1)) & 1u ? p1 : 0.f;
-                p2 = (w >> (c + 2)) & 1u ? p2 : 0.f; p3 = (w >> (c + 3)) & 1u ? p3 : 0.f;
+              // A masked pair gets the exponent -inf: ONE select per element, ahead of the exp2 (P = 0 and with it
+              // dS = P (dP - delta) = 0).  Selecting P after the exp2 let the compiler hoist the dS product above the
+              // branch and select P and dS separately (ncu: 1.6 FSEL per element in this kernel).
+              float a0 = fmaf(s[c], kScaleLog2, -l4.x), a1 = fmaf(s[c + 1], kScaleLog2, -l4.y);
+              float a2 = fmaf(s[c + 2], kScaleLog2, -l4.z), a3 = fmaf(s[c + 3], kScaleLog2, -l4.w);
+              if (!clean) {
+                const float ninf = __int_as_float(0xff800000);
+                a0 = (w >> c) & 1u ? a0 : ninf; a1 = (w >> (c + 1)) & 1u ? a1 : ninf;
+                a2 = (w >> (c + 2)) & 1u ? a2 : ninf; a3 = (w >> (c + 3)) & 1u ? a3 : ninf;
               }
+              p0 = ex2(a0); p1 = ex2(a1); p2 = ex2(a2); p3 = ex2(a3);
               g0 = p0 * fmaf(dp[c], kScale, -d4.x); g1 = p1 * fmaf(dp[c + 1], kScale, -d4.y);
               g2 = p2 * fmaf(dp[c + 2], kScale, -d4.z); g3 = p3 * fmaf(dp[c + 3], kScale, -d4.w);
             }
@@ -1026,13 +1045,15 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
             pd[(c >> 1) + 1] = pack_bf16(g2, g3);
           }
         }
+        tmem_st_32x16(t_b + half * 32, pp);        // Pt over this thread's own St columns
+        tmem_st_32x16(t_b + 64 + half * 32, pd);   // dSt over its own dPt columns
       }
-      tmem_st_32x16(t_b + half * 32, pp);        // Pt over this thread's own St columns
-      tmem_st_32x16(t_b + 64 + half * 32, pd);   // dSt over its own dPt columns
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_p[buf]);  // one arrival per warp: 8 instead of 256 serialised updates of one mbarrier
+      if (++qi == n_q) { qi = 0; tile0 = q_lo * 64; } else tile0 += 64;
+      if (buf == 0) buf = 2; else { --buf; spar ^= 1u; }   // v += 2
     }
     // the accumulate MMAs must have retired; slot 0's warps store dV, slot 1's store dK
     mbar_wait(bar_done, 0);

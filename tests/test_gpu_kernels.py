@@ -221,6 +221,88 @@ def test_gemm_device_side_limits():
         assert float((out - ref2).abs().max()) <= 1e-5 * max(1.0, float(ref2.abs().max())), (count, sk)
 
 
+def test_gemm_cta_pairs():
+    """Shapes that take the CTA-pair kernels (M >= 512, 256-wide tiles: one 256 x 256 tile over the two SMs of a TPC): the
+    four operand layouts with ragged M / N / K, bf16 and fused epilogues bit-identical to the stand-alone kernels, split-K,
+    and the device-side row limit at its 128-row granularity (one CTA of a pair live, the other not)."""
+    for (M, N, K) in ((1000, 512, 320), (512, 256, 64), (2048, 1280, 136), (1304, 776, 200)):
+        A = g_randn(M, K, seed=1).bfloat16(); B = g_randn(N, K, seed=2).bfloat16()
+        ref = A.float() @ B.float().t()
+        for a_k, b_k in ((1, 1), (1, 0), (0, 1), (0, 0)):
+            As = A.contiguous() if a_k else A.t().contiguous()
+            Bs = B.contiguous() if b_k else B.t().contiguous()
+            out = torch.full((M, N), float("nan"), device=DEV)
+            L.gemm(As, Bs, out, M, N, K, a_kmajor=bool(a_k), b_kmajor=bool(b_k), epilogue=L.EPI_F32)
+            report(f"pair gemm a_k={a_k} b_k={b_k} {M}x{N}x{K}", out, ref, 1e-5)
+        ob = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+        L.gemm(A, B, ob, M, N, K)
+        assert torch.equal(ob, ref.bfloat16()) or rel_err(ob, ref) < 4e-3
+    # many tiles per pair (persistent loop, both accumulator stages, ring wrap-around) and split-K over pairs
+    M, N, K = 768, 512, 16384
+    A = g_randn(K, M, seed=3).bfloat16(); B = g_randn(K, N, seed=4).bfloat16()
+    ref = A.float().t() @ B.float()
+    for sk in (-1, 4, 0):
+        out = torch.full((M, N), float("nan"), device=DEV)
+        L.gemm(A, B, out, M, N, K, a_kmajor=False, b_kmajor=False, epilogue=L.EPI_F32, split_k=sk)
+        report(f"pair split_k={sk}", out, ref, 2e-5)
+    M, N, K = 8192, 1024, 256
+    A = g_randn(M, K, seed=5).bfloat16(); B = g_randn(N, K, seed=6).bfloat16()
+    out = torch.empty(M, N, device=DEV)
+    L.gemm(A, B, out, M, N, K, epilogue=L.EPI_F32)
+    report("pair persistent", out, A.float() @ B.float().t(), 1e-5)
+    # device-side row limit
+    M, N, K = 1024, 512, 128
+    A = g_randn(M, K, seed=7).bfloat16(); B = g_randn(N, K, seed=8).bfloat16()
+    ref = A.float() @ B.float().t()
+    for count in (0, 1, 128, 130, 300, 512, 1000, 9999):
+        cnt = torch.tensor([count], dtype=torch.int32, device=DEV)
+        out = torch.full((M, N), -7.0, device=DEV)
+        L.gemm(A, B, out, M, N, K, epilogue=L.EPI_F32, m_count=cnt)
+        lim = min(M, (count + 127) // 128 * 128)
+        report(f"pair m_count {count}", out[:lim], ref[:lim], 1e-5) if lim else None
+        assert bool((out[lim:] == -7.0).all()), count
+    # fused SwiGLU epilogue == plain GEMM + stand-alone kernel
+    M, K, I = 1100, 192, 320
+    A = g_randn(M, K, seed=21).bfloat16()
+    w1 = g_randn(I, K, seed=22, scale=0.2).bfloat16(); w3 = g_randn(I, K, seed=23, scale=0.2).bfloat16()
+    gu_ref = torch.empty(M, 2 * I, device=DEV, dtype=torch.bfloat16)
+    L.gemm(A, torch.cat([w1, w3]).contiguous(), gu_ref, M, 2 * I, K)
+    act_ref = torch.empty(M, I, device=DEV, dtype=torch.bfloat16); L.swiglu_fwd(gu_ref, act_ref)
+    w13 = torch.stack([w1.view(I // 64, 64, K), w3.view(I // 64, 64, K)], 1).reshape(2 * I, K).contiguous()
+    gu = torch.empty(M, 2 * I, device=DEV, dtype=torch.bfloat16)
+    act = torch.full((M, I), float("nan"), device=DEV, dtype=torch.bfloat16)
+    L.gemm(A, w13, gu, M, 2 * I, K, epilogue=L.EPI_SWIGLU, aux=act, ldaux=I)
+    guv = gu.view(M, I // 64, 2, 64)
+    assert torch.equal(guv[:, :, 0].reshape(M, I), gu_ref[:, :I]) and torch.equal(guv[:, :, 1].reshape(M, I), gu_ref[:, I:])
+    assert torch.equal(act, act_ref)
+    # fused RoPE epilogue
+    rows, row_len, H, G = 3, 256, 6, 1
+    T, N = rows * row_len, (H + 2 * G) * 64
+    X = g_randn(T, K, seed=25).bfloat16(); Wq = g_randn(N, K, seed=26, scale=0.2).bfloat16()
+    inv = 1.0 / (500000.0 ** (torch.arange(0, 64, 2).float() / 64))
+    ang = torch.outer(torch.arange(row_len).float(), inv)
+    cos, sin = torch.cos(ang).to(DEV).contiguous(), torch.sin(ang).to(DEV).contiguous()
+    ref = torch.empty(T, N, device=DEV, dtype=torch.bfloat16)
+    L.gemm(X, Wq, ref, T, N, K); L.rope(ref, H + G, row_len, cos, sin)
+    got = torch.empty(T, N, device=DEV, dtype=torch.bfloat16)
+    L.gemm(X, Wq, got, T, N, K, epilogue=L.EPI_ROPE, rope=dict(cos=cos, sin=sin, cols=(H + G) * 64, row_len=row_len))
+    assert torch.equal(got, ref)
+    # fused cross-entropy over a catalog (row count from the device: one CTA of the last pair idle)
+    M, N, K = 1024, 3000, 128
+    h = g_randn(M, K, seed=31).bfloat16(); items = (g_randn(N, K, seed=32) * 0.3).bfloat16()
+    tgt_idx = torch.randint(0, N, (M,), generator=torch.Generator().manual_seed(5)).int().to(DEV)
+    logits = (h.float() @ items.float().t()).bfloat16().float()
+    nb = L.ce_nblocks(N)
+    cnt = torch.tensor([700], dtype=torch.int32, device=DEV)
+    pmax = torch.full((nb, M), 7.0, device=DEV); psum = torch.full((nb, M), 7.0, device=DEV); tgt = torch.zeros(M, device=DEV)
+    L.gemm(h, items, None, M, N, K, epilogue=L.EPI_CE_PARTIAL, ce=dict(pmax=pmax, psum=psum, tgt=tgt, target=tgt_idx), m_count=cnt)
+    mo = torch.empty(M, device=DEV); so = torch.empty(M, device=DEV)
+    L.ce_merge_partials(pmax, psum, nb, mo, so)
+    # 3 M logits: a few land on the other side of a bf16 rounding boundary than torch's fp32 matmul (0.06 x their softmax weight)
+    assert float((mo + so.log() - torch.logsumexp(logits, 1))[:700].abs().max()) < 1e-3
+    assert float((tgt - logits[torch.arange(M), tgt_idx.long()])[:700].abs().max()) < 0.02   # one bf16 ulp of a logit
+
+
 def test_gemm_fused_cross_entropy_catalog_slices():
     """CE_PARTIAL on catalog slices as the vocab-parallel head cuts them: widths below one tile / one chunk, targets that
     lie outside the slice (they must not match any column: the shard owning them reports the target logit)."""

@@ -1,0 +1,7 @@
+#!/bin/bash
+# ncu --set full (with source) of one fused d(act) + SwiGLU-backward GEMM launch after a plain run of the same command
+mkdir -p gpurun_out
+C="python tools/swb_time.py"
+timeout 300 $C > gpurun_out/plain.log 2>&1 &&
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gemm_bf16_kernel" -s 3 -c 1 -f -o gpurun_out/prof_swb $C > gpurun_out/ncu_swb.log 2>&1
+echo "== ncu exit $?"; tail -2 gpurun_out/plain.log; tail -3 gpurun_out/ncu_swb.log
