@@ -171,7 +171,10 @@ __device__ __forceinline__ void cluster_sync_all() {  // every thread of both CT
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(bar)), "r"(cta));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+  // default semantics (.release.cta), as CUTLASS's ClusterBarrier::arrive(cta_id): with .release.cluster ptxas emits
+  // MEMBAR.ALL.GPU + ERRBAR in front of the arrive (ncu: 16 % of the fused SwiGLU-backward GEMM's stall samples); what the
+  // arrive publishes here are completed tcgen05.ld reads, ordered by tcgen05.fence::before_thread_sync, not global memory
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
 }
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem) {  // the same warp of BOTH CTAs
