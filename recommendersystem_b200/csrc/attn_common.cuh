@@ -39,6 +39,16 @@ __device__ __forceinline__ void tmem_ld_32x32_f(uint32_t taddr, float (&v)[32]) 
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+// two 32-column loads in flight, one wait: the second load's latency hides behind the first's
+__device__ __forceinline__ void tmem_ld_32x32_f2(uint32_t taddr_a, float (&a)[32], uint32_t taddr_b, float (&b)[32]) {
+  uint32_t ra[32], rb[32];
+  tmem_ld_32x32(taddr_a, ra);
+  tmem_ld_32x32(taddr_b, rb);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { a[j] = __uint_as_float(ra[j]); b[j] = __uint_as_float(rb[j]); }
+}
+
 // bits [lo,hi) of the tile's columns that fall into 32-column word w
 __device__ __forceinline__ uint32_t range_word(int lo, int hi, int w) {
   const int a = min(max(lo - 32 * w, 0), 32), b = min(max(hi - 32 * w, 0), 32);

@@ -50,6 +50,18 @@ constexpr int PAIR_THREADS = 576;  // 16 softmax warps, MMA issue warp (16), TMA
 // ATTN_POLY = n > 0: in the forward kernel's unmasked path every n-th pair of exponentials is evaluated on the FMA pipe
 // (Cody-Waite split + degree-3 polynomial, rel. error 6e-4 << bf16's 4e-3) instead of the MUFU: the exp passes are MUFU-bound
 // (16 lanes per SM), the FMA pipe idles.  0 = off.
+#ifndef ATTN_LD_PAIR
+#define ATTN_LD_PAIR 1   // backward: the S and dP loads of a step in flight together (one tcgen05.wait::ld)
+#endif
+#ifndef ATTN_BWD_X8
+#define ATTN_BWD_X8 0   // pipelined 8-column passes: measured slower than 16-column passes (2077 vs 2063 us)
+#endif
+#ifndef ATTN_DQ_X16
+#define ATTN_DQ_X16 0   // 16-column passes in dQ: measured slower (2112 vs 2066 us); dK/dV gains 2.6 % from them
+#endif
+#ifndef ATTN_DKV_X16
+#define ATTN_DKV_X16 1
+#endif
 #ifndef ATTN_POLY
 #define ATTN_POLY 0
 #endif
@@ -739,10 +751,85 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
         for (int q = 0; q < 16; ++q) zr[q] = 0u;
         tmem_st_32x16(t_b + half * 32, zr);
       } else {
+#if ATTN_BWD_X8
+        // four passes of 8 key columns, the next pass's S / dP columns in flight while this one is worked on (see dK/dV)
+        uint32_t rs[2][8], rd[2][8];
+        tmem_ld_32x8(t_b + half * 32, rs[0]);
+        tmem_ld_32x8(t_b + 64 + half * 32, rd[0]);
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+          tmem_ld_wait();
+          if (ps < 3) {
+            tmem_ld_32x8(t_b + half * 32 + (ps + 1) * 8, rs[(ps + 1) & 1]);
+            tmem_ld_32x8(t_b + 64 + half * 32 + (ps + 1) * 8, rd[(ps + 1) & 1]);
+          }
+          const uint32_t (&cs)[8] = rs[ps & 1];
+          const uint32_t (&cd)[8] = rd[ps & 1];
+          uint32_t pk[4];
+          const uint32_t wb = (w >> (8 * ps)) & 0xffu;
+          const bool clean = __all_sync(0xffffffffu, wb == 0xffu);
+#pragma unroll
+          for (int c = 0; c < 8; c += 2) {
+            const int cg = 8 * ps + c;
+            const float s0 = __uint_as_float(cs[c]), s1 = __uint_as_float(cs[c + 1]);
+            const float e0 = __uint_as_float(cd[c]), e1 = __uint_as_float(cd[c + 1]);
+            if (SILU) {
+              float d0 = silu_grad_fast(s0 * kScale) * e0 * gs_n, d1 = silu_grad_fast(s1 * kScale) * e1 * gs_n;
+              if (!clean) { d0 = (w >> cg) & 1u ? d0 : 0.f; d1 = (w >> (cg + 1)) & 1u ? d1 : 0.f; }
+              pk[c >> 1] = pack_bf16(d0, d1);
+            } else {
+              float a0 = fmaf(s0, kScaleLog2, -lse2), a1 = fmaf(s1, kScaleLog2, -lse2);
+              if (!clean) {   // one select per masked element, ahead of the exp2
+                const float ninf = __int_as_float(0xff800000);
+                a0 = (w >> cg) & 1u ? a0 : ninf; a1 = (w >> (cg + 1)) & 1u ? a1 : ninf;
+              }
+              pk[c >> 1] = pack_bf16(ex2(a0) * fmaf(e0, kScale, -dlt_s), ex2(a1) * fmaf(e1, kScale, -dlt_s));
+            }
+          }
+          tmem_st_32x4(t_b + half * 32 + ps * 4, pk);   // over this thread's own (already read) score columns
+        }
+#elif ATTN_DQ_X16
+        // two passes of 16 key columns (half the live registers; see dK/dV)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t cs[16], cd[16], pk[8];
+          tmem_ld_32x16(t_b + half * 32 + hf * 16, cs);
+          tmem_ld_32x16(t_b + 64 + half * 32 + hf * 16, cd);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {
+            const uint32_t wb = (w >> (16 * hf + 8 * g8)) & 0xffu;
+            const bool clean = __all_sync(0xffffffffu, wb == 0xffu);
+#pragma unroll
+            for (int c = 8 * g8; c < 8 * g8 + 8; c += 2) {
+              const int cg = 16 * hf + c;
+              const float s0 = __uint_as_float(cs[c]), s1 = __uint_as_float(cs[c + 1]);
+              const float e0 = __uint_as_float(cd[c]), e1 = __uint_as_float(cd[c + 1]);
+              if (SILU) {
+                float d0 = silu_grad_fast(s0 * kScale) * e0 * gs_n, d1 = silu_grad_fast(s1 * kScale) * e1 * gs_n;
+                if (!clean) { d0 = (w >> cg) & 1u ? d0 : 0.f; d1 = (w >> (cg + 1)) & 1u ? d1 : 0.f; }
+                pk[c >> 1] = pack_bf16(d0, d1);
+              } else {
+                float a0 = fmaf(s0, kScaleLog2, -lse2), a1 = fmaf(s1, kScaleLog2, -lse2);
+                if (!clean) {   // one select per masked element, ahead of the exp2
+                  const float ninf = __int_as_float(0xff800000);
+                  a0 = (w >> cg) & 1u ? a0 : ninf; a1 = (w >> (cg + 1)) & 1u ? a1 : ninf;
+                }
+                pk[c >> 1] = pack_bf16(ex2(a0) * fmaf(e0, kScale, -dlt_s), ex2(a1) * fmaf(e1, kScale, -dlt_s));
+              }
+            }
+          }
+          tmem_st_32x8(t_b + half * 32 + hf * 8, pk);   // over this thread's own (already read) score columns
+        }
+#else
         uint32_t pk[16];
         float s[32], dp[32];
+#if ATTN_LD_PAIR
+        tmem_ld_32x32_f2(t_b + half * 32, s, t_b + 64 + half * 32, dp);
+#else
         tmem_ld_32x32_f(t_b + half * 32, s);
         tmem_ld_32x32_f(t_b + 64 + half * 32, dp);
+#endif
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
           const uint32_t wb = (w >> (8 * g8)) & 0xffu;
@@ -772,6 +859,7 @@ attn_dq_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_c
           }
         }
         tmem_st_32x16(t_b + half * 32, pk);   // over this thread's own (already read) score columns
+#endif
       }
       tmem_st_wait();
       tc_fence_before();
@@ -1000,10 +1088,126 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
         tmem_st_32x16(t_b + half * 32, zr);
         tmem_st_32x16(t_b + 64 + half * 32, zr);
       } else {
+#if ATTN_BWD_X8
+        // four passes of 8 query columns, the next pass's S / dP columns in flight while this one is worked on (40 live
+        // registers instead of 96); a pass's packed Pt / dSt land in St / dPt columns an earlier pass has already read
+        uint32_t rs[2][8], rd[2][8];
+        tmem_ld_32x8(t_b + half * 32, rs[0]);
+        tmem_ld_32x8(t_b + 64 + half * 32, rd[0]);
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+          tmem_ld_wait();
+          if (ps < 3) {
+            tmem_ld_32x8(t_b + half * 32 + (ps + 1) * 8, rs[(ps + 1) & 1]);
+            tmem_ld_32x8(t_b + 64 + half * 32 + (ps + 1) * 8, rd[(ps + 1) & 1]);
+          }
+          const uint32_t (&cs)[8] = rs[ps & 1];
+          const uint32_t (&cd)[8] = rd[ps & 1];
+          uint32_t pp[4], pd[4];
+          const uint32_t wb = (w >> (8 * ps)) & 0xffu;
+          const bool clean = __all_sync(0xffffffffu, wb == 0xffu);
+#pragma unroll
+          for (int c = 0; c < 8; c += 4) {
+            const int cg = 8 * ps + c;   // column inside the warp's 32
+            const float4 l4 = SILU ? make_float4(0.f, 0.f, 0.f, 0.f) : sl[cg >> 2];
+            const float4 d4 = SILU ? make_float4(0.f, 0.f, 0.f, 0.f) : sd[cg >> 2];
+            const float s0 = __uint_as_float(cs[c]), s1 = __uint_as_float(cs[c + 1]), s2 = __uint_as_float(cs[c + 2]), s3 = __uint_as_float(cs[c + 3]);
+            const float e0 = __uint_as_float(cd[c]), e1 = __uint_as_float(cd[c + 1]), e2 = __uint_as_float(cd[c + 2]), e3 = __uint_as_float(cd[c + 3]);
+            float p0, p1, p2, p3, g0, g1, g2, g3;
+            if (SILU) {
+              const float z0 = s0 * kScale, z1 = s1 * kScale, z2 = s2 * kScale, z3 = s3 * kScale;
+              p0 = silu_fast(z0) * inv_n; p1 = silu_fast(z1) * inv_n; p2 = silu_fast(z2) * inv_n; p3 = silu_fast(z3) * inv_n;
+              const float gn = kScale * inv_n;
+              g0 = silu_grad_fast(z0) * e0 * gn; g1 = silu_grad_fast(z1) * e1 * gn;
+              g2 = silu_grad_fast(z2) * e2 * gn; g3 = silu_grad_fast(z3) * e3 * gn;
+              if (!clean) {
+                const bool b0 = (w >> cg) & 1u, b1 = (w >> (cg + 1)) & 1u, b2 = (w >> (cg + 2)) & 1u, b3 = (w >> (cg + 3)) & 1u;
+                p0 = b0 ? p0 : 0.f; p1 = b1 ? p1 : 0.f; p2 = b2 ? p2 : 0.f; p3 = b3 ? p3 : 0.f;
+                g0 = b0 ? g0 : 0.f; g1 = b1 ? g1 : 0.f; g2 = b2 ? g2 : 0.f; g3 = b3 ? g3 : 0.f;
+              }
+            } else {
+              float a0 = fmaf(s0, kScaleLog2, -l4.x), a1 = fmaf(s1, kScaleLog2, -l4.y);
+              float a2 = fmaf(s2, kScaleLog2, -l4.z), a3 = fmaf(s3, kScaleLog2, -l4.w);
+              if (!clean) {   // one select per masked element, ahead of the exp2 (see the 32-column form below)
+                const float ninf = __int_as_float(0xff800000);
+                a0 = (w >> cg) & 1u ? a0 : ninf; a1 = (w >> (cg + 1)) & 1u ? a1 : ninf;
+                a2 = (w >> (cg + 2)) & 1u ? a2 : ninf; a3 = (w >> (cg + 3)) & 1u ? a3 : ninf;
+              }
+              p0 = ex2(a0); p1 = ex2(a1); p2 = ex2(a2); p3 = ex2(a3);
+              g0 = p0 * fmaf(e0, kScale, -d4.x); g1 = p1 * fmaf(e1, kScale, -d4.y);
+              g2 = p2 * fmaf(e2, kScale, -d4.z); g3 = p3 * fmaf(e3, kScale, -d4.w);
+            }
+            pp[c >> 1] = pack_bf16(p0, p1);
+            pp[(c >> 1) + 1] = pack_bf16(p2, p3);
+            pd[c >> 1] = pack_bf16(g0, g1);
+            pd[(c >> 1) + 1] = pack_bf16(g2, g3);
+          }
+          tmem_st_32x4(t_b + half * 32 + ps * 4, pp);        // Pt over this thread's own St columns
+          tmem_st_32x4(t_b + 64 + half * 32 + ps * 4, pd);   // dSt over its own dPt columns
+        }
+#elif ATTN_DKV_X16
+        // two passes of 16 query columns: half the live registers of the 32-column form (96 registers per thread: 5 warps per
+        // scheduler), so the compiler can keep more independent elements in flight; a pass's packed Pt / dSt land in St / dPt
+        // columns the same pass has already read
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t rs[16], rd[16], pp[8], pd[8];
+          tmem_ld_32x16(t_b + half * 32 + hf * 16, rs);
+          tmem_ld_32x16(t_b + 64 + half * 32 + hf * 16, rd);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {
+            const uint32_t wb = (w >> (16 * hf + 8 * g8)) & 0xffu;
+            const bool clean = __all_sync(0xffffffffu, wb == 0xffu);
+#pragma unroll
+            for (int c = 8 * g8; c < 8 * g8 + 8; c += 4) {
+              const int cg = 16 * hf + c;   // column inside the warp's 32
+              const float4 l4 = SILU ? make_float4(0.f, 0.f, 0.f, 0.f) : sl[cg >> 2];
+              const float4 d4 = SILU ? make_float4(0.f, 0.f, 0.f, 0.f) : sd[cg >> 2];
+              const float s0 = __uint_as_float(rs[c]), s1 = __uint_as_float(rs[c + 1]), s2 = __uint_as_float(rs[c + 2]), s3 = __uint_as_float(rs[c + 3]);
+              const float e0 = __uint_as_float(rd[c]), e1 = __uint_as_float(rd[c + 1]), e2 = __uint_as_float(rd[c + 2]), e3 = __uint_as_float(rd[c + 3]);
+              float p0, p1, p2, p3, g0, g1, g2, g3;
+              if (SILU) {
+                const float z0 = s0 * kScale, z1 = s1 * kScale, z2 = s2 * kScale, z3 = s3 * kScale;
+                p0 = silu_fast(z0) * inv_n; p1 = silu_fast(z1) * inv_n; p2 = silu_fast(z2) * inv_n; p3 = silu_fast(z3) * inv_n;
+                const float gn = kScale * inv_n;
+                g0 = silu_grad_fast(z0) * e0 * gn; g1 = silu_grad_fast(z1) * e1 * gn;
+                g2 = silu_grad_fast(z2) * e2 * gn; g3 = silu_grad_fast(z3) * e3 * gn;
+                if (!clean) {
+                  const bool b0 = (w >> cg) & 1u, b1 = (w >> (cg + 1)) & 1u, b2 = (w >> (cg + 2)) & 1u, b3 = (w >> (cg + 3)) & 1u;
+                  p0 = b0 ? p0 : 0.f; p1 = b1 ? p1 : 0.f; p2 = b2 ? p2 : 0.f; p3 = b3 ? p3 : 0.f;
+                  g0 = b0 ? g0 : 0.f; g1 = b1 ? g1 : 0.f; g2 = b2 ? g2 : 0.f; g3 = b3 ? g3 : 0.f;
+                }
+              } else {
+                float a0 = fmaf(s0, kScaleLog2, -l4.x), a1 = fmaf(s1, kScaleLog2, -l4.y);
+                float a2 = fmaf(s2, kScaleLog2, -l4.z), a3 = fmaf(s3, kScaleLog2, -l4.w);
+                if (!clean) {   // one select per masked element, ahead of the exp2 (see the 32-column form below)
+                  const float ninf = __int_as_float(0xff800000);
+                  a0 = (w >> cg) & 1u ? a0 : ninf; a1 = (w >> (cg + 1)) & 1u ? a1 : ninf;
+                  a2 = (w >> (cg + 2)) & 1u ? a2 : ninf; a3 = (w >> (cg + 3)) & 1u ? a3 : ninf;
+                }
+                p0 = ex2(a0); p1 = ex2(a1); p2 = ex2(a2); p3 = ex2(a3);
+                g0 = p0 * fmaf(e0, kScale, -d4.x); g1 = p1 * fmaf(e1, kScale, -d4.y);
+                g2 = p2 * fmaf(e2, kScale, -d4.z); g3 = p3 * fmaf(e3, kScale, -d4.w);
+              }
+              pp[c >> 1] = pack_bf16(p0, p1);
+              pp[(c >> 1) + 1] = pack_bf16(p2, p3);
+              pd[c >> 1] = pack_bf16(g0, g1);
+              pd[(c >> 1) + 1] = pack_bf16(g2, g3);
+            }
+          }
+          tmem_st_32x8(t_b + half * 32 + hf * 8, pp);        // Pt over this thread's own St columns
+          tmem_st_32x8(t_b + 64 + half * 32 + hf * 8, pd);   // dSt over its own dPt columns
+        }
+#else
         uint32_t pp[16], pd[16];
         float s[32], dp[32];
+#if ATTN_LD_PAIR
+        tmem_ld_32x32_f2(t_b + half * 32, s, t_b + 64 + half * 32, dp);
+#else
         tmem_ld_32x32_f(t_b + half * 32, s);
         tmem_ld_32x32_f(t_b + 64 + half * 32, dp);
+#endif
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
           const uint32_t wb = (w >> (8 * g8)) & 0xffu;
@@ -1047,6 +1251,7 @@ attn_dkv_pair_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_
         }
         tmem_st_32x16(t_b + half * 32, pp);        // Pt over this thread's own St columns
         tmem_st_32x16(t_b + 64 + half * 32, pd);   // dSt over its own dPt columns
+#endif
       }
       tmem_st_wait();
       tc_fence_before();
