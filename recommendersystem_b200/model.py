@@ -634,10 +634,10 @@ class _ClozeStep(torch.autograd.Function):
                 L.gemm(hs_rows, items, dlog, rows_n, cn, dm, ldc=CH, epilogue=L.EPI_CE_GRAD,
                        ce=dict(lse=lse_rows, coef=coef_rows, target=tgt_rows), n_offset=c0, m_count=lim)
                 # d hidden rows += dlogits . items
-                # (only ~2350 / ~1550 of the 8192 rows are live: 10 / 7 row blocks of 256 x 3 column blocks on 74 SM pairs; seven
-                # K splits give 210 / 147 work units = 2.84 / 1.99 waves - five gave 2.03 / 1.42, i.e. a nearly empty last wave)
+                # (only ~2350 / ~1550 of the 8192 rows are live: 10 / 7 row blocks of 256 x 3 column blocks; five K splits.  Seven
+                # (210 / 147 work units = 2.84 / 1.99 waves on 74 SM pairs instead of 2.03 / 1.42) measured no better: 572 vs 603 TFLOP/s)
                 L.gemm(dlog, items, dhs, rows_n, dm, cn, lda=CH, b_kmajor=False, ldb=dm,
-                       epilogue=L.EPI_F32 if c0 == 0 else L.EPI_F32_ACCUM, m_count=lim, split_k=7 if cn >= 4096 else 0)
+                       epilogue=L.EPI_F32 if c0 == 0 else L.EPI_F32_ACCUM, m_count=lim, split_k=5 if cn >= 4096 else 0)
                 # d table rows = dlogits^T . hidden rows
                 if tab:
                     L.gemm(dlog, hs_rows, dtable[c_lo + c0: c_lo + c0 + cn], cn, dm, rows_n, a_kmajor=False, lda=CH,
