@@ -3,11 +3,12 @@
 //   warp 1   : tcgen05.mma issuer (one thread), fp32 accumulators in TMEM,
 //              two accumulator stages so the epilogue of tile i overlaps tile i+1
 //   warp 2   : TMEM allocator
-//   warps 4-7: epilogue, tcgen05.ld 32x32b (thread = accumulator row) -> fused
-//              epilogue -> global
-// Tile 128 x BN x 64 (BN = 256 or 128); operands K-major or MN-major straight
-// from row-major tensors (no transposed copies); optional split-K into fp32
-// partials reduced in a fixed order.
+//   warps 4-11: epilogue (two warps per TMEM lane quarter), tcgen05.ld 32x32b
+//              (thread = accumulator row) -> fused epilogue -> TMA store / global
+// Tile 128 x BN x 64 per CTA (BN = 256 or 128), or 256 x 256 x 64 on a CTA pair
+// (CTA2: cluster of two, tcgen05 cta_group::2; see GemmSmem); operands K-major or
+// MN-major straight from row-major tensors (no transposed copies); optional
+// split-K into fp32 partials reduced in a fixed order.
 #include "common.cuh"
 
 namespace graft {

@@ -104,10 +104,11 @@ def test_gemm_split_plan_host():
         assert need % (M * N * 4) == 0
         return need // (M * N * 4)
 
-    assert splits(768, 2112, 131072) == 8      # 54 tiles -> 432 work units = 2.9 rounds of 148 SMs (was 2 splits: 108 units)
-    assert splits(4224, 768, 131072) == 7      # 99 tiles -> 693 units = 4.7 rounds (was unsplit: 99 units)
-    assert splits(1536, 768, 131072) == 4      # 36 tiles -> 144 units
-    assert splits(768, 768, 131072) == 8       # 18 tiles -> 144 units
+    # 256 x 256 tiles on the 74 SM pairs of a 148-SM part (one-CTA 128 x 256 tiles on 148 SMs give the same counts)
+    assert splits(768, 2112, 131072) == 8      # 27 pair tiles -> 216 work units = 2.9 rounds of 74 pairs
+    assert splits(4224, 768, 131072) == 7      # 51 pair tiles -> 357 units = 4.8 rounds
+    assert splits(1536, 768, 131072) == 4      # 18 pair tiles -> 72 units: one round
+    assert splits(768, 768, 131072) == 8       # 9 pair tiles -> 72 units
     assert splits(768, 6148, 100001) == 0      # 128-wide tiles: 294 tiles = 2 full rounds, no split needed
     assert splits(768, 2112, 131072, split_k=0) == 0 and splits(768, 2112, 131072, split_k=3) == 3
     assert splits(768, 2112, 131072, epilogue=L.EPI_BF16) == 0   # only fp32 outputs are split
